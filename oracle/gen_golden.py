@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz by executing the GENUINE
+reference (loaded from /root/reference by oracle/ref_loader.py) on seeded inputs.
+
+Run in the build container:  python -m oracle.gen_golden
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _coherent_feats(g, T, C, H, W, relu=True):
+    """temporally coherent, spatially smooth features (near-ties like encoder output)."""
+    base = torch.randn(C, H // 2 + 2, W // 2 + 2, generator=g)
+    frames = []
+    for t in range(T):
+        base = base + 0.15 * torch.randn(base.shape, generator=g)
+        f = torch.nn.functional.interpolate(base[None], size=(H, W), mode="bilinear",
+                                            align_corners=False)[0]
+        f = f + 0.05 * torch.randn(f.shape, generator=g)
+        frames.append(f.relu() if relu else f)
+    return torch.stack(frames)  # [T,C,H,W]
+
+
+def gen_propagate(ref):
+    cases = []
+    specs = [
+        # name, H, W, C, T, L, neighbor_range, topk, non_mask_len, coherent
+        ("rand_small", 12, 14, 32, 3, 5, 8, 5, 0, False),
+        ("rand_nonmask1", 10, 9, 32, 4, 3, 6, 10, 1, False),
+        ("coh_dupframe0", 16, 20, 64, 4, 6, 10, 10, 0, True),
+        ("coh_c256", 15, 27, 256, 6, 8, 24, 10, 0, True),
+        ("tiny_fewcands", 5, 6, 32, 1, 2, 2, 10, 0, False),   # r=1: 1 in-mask key < k
+    ]
+    for i, (name, H, W, C, T, L, nr, k, nml, coh) in enumerate(specs):
+        g = torch.Generator().manual_seed(100 + i)
+        if coh:
+            f = _coherent_feats(g, T + 1, C, H, W)
+            q, kf = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+            if name == "coh_dupframe0":   # memory = [0, 0, 1, 2]: frame 0 twice
+                kf = torch.cat([kf[:, :, :1], kf[:, :, :T - 1]], dim=2)
+        else:
+            q = torch.randn(1, C, H, W, generator=g)
+            kf = torch.randn(1, C, T, H, W, generator=g)
+        v = torch.rand(1, L, T, H, W, generator=g)
+        if name == "coh_dupframe0":
+            v = torch.cat([v[:, :, :1], v[:, :, :T - 1]], dim=2)
+        mask = ref.spatial_neighbor(1, H, W, neighbor_range=nr, device="cpu", dtype=torch.float32)
+        o1 = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=k, step=64,
+                                            non_mask_len=nml)
+        o2 = ref.masked_attention_efficient_v2(q, kf, v, nr // 2, temperature=0.07, topk=k, step=64)
+        cases.append(name)
+        np.savez_compressed(os.path.join(OUT, f"prop_{name}.npz"), q=q.numpy(), k=kf.numpy(),
+                            v=v.numpy(), neighbor_range=nr, topk=k, non_mask_len=nml,
+                            temperature=0.07, out_v1=o1.numpy(), out_v2=o2.numpy())
+    return cases
+
+
+def gen_masks(ref):
+    d = {}
+    for (H, W, nr) in [(6, 7, 4), (9, 5, 7), (12, 14, 8)]:
+        d[f"circle_{H}_{W}_{nr}"] = ref.spatial_neighbor(1, H, W, nr, "cpu", torch.float32).numpy()
+        d[f"square_{H}_{W}_{nr}"] = ref.spatial_neighbor(1, H, W, nr, "cpu", torch.float32,
+                                                         mode="square")[0].bool().numpy()
+    np.savez_compressed(os.path.join(OUT, "masks.npz"), **d)
+
+
+def gen_c2f(ref):
+    g = torch.Generator().manual_seed(7)
+    Hc, Wc, s, T, C, Cf, L, rf = 6, 7, 4, 3, 32, 16, 4, 3
+    f = _coherent_feats(g, T + 1, C, Hc, Wc)
+    ff = _coherent_feats(g, T + 1, Cf, Hc * s, Wc * s)
+    q, k = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+    qf, kf = ff[T][None], ff[:T].permute(1, 0, 2, 3)[None].contiguous()
+    v = torch.rand(1, L, T, Hc * s, Wc * s, generator=g)
+    mask = ref.spatial_neighbor(1, Hc, Wc, neighbor_range=6, device="cpu", dtype=torch.float32)
+    o = ref.masked_attention_efficient_c2f(q, k, qf, kf, v, mask, temperature=0.07, topk=10,
+                                           step=16, radius_fine=rf)
+    np.savez_compressed(os.path.join(OUT, "c2f_small.npz"), q=q.numpy(), k=k.numpy(),
+                        qf=qf.numpy(), kf=kf.numpy(), v=v.numpy(), neighbor_range=6, topk=10,
+                        temperature=0.07, radius_fine=rf, out=o.numpy())
+
+
+def gen_legacy(ref):
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(2, 16, 5, 6, generator=g)
+    b = torch.randn(2, 16, 5, 6, generator=g)
+    img = torch.rand(2, 3, 5, 6, generator=g)
+    aff = ref.compute_affinity(a, b, temperature=0.07, softmax_dim=1)
+    prop = ref.propagate(img, aff.clone(), topk=4)
+    np.savez_compressed(os.path.join(OUT, "legacy.npz"), a=a.numpy(), b=b.numpy(), img=img.numpy(),
+                        aff=aff.numpy(), prop=prop.numpy())
+
+
+def gen_tracker():
+    """Genuine VanillaTracker.forward_test + genuine random-init ResNet-18 (seed 0)."""
+    trk = ref_loader.load_tracker()
+    out = {}
+    for tag, strides, hw, nr in [("s8", (1, 2, 2, 1), (64, 96), 8), ("s2", (1, 1, 1, 4), (32, 40), 12)]:
+        cfg = trk.TestCfg(precede_frames=2, topk=10, temperature=0.07, neighbor_range=nr, step=64,
+                          with_first=True, with_first_neighbor=True)
+        torch.manual_seed(0)
+        model = trk.VanillaTracker(backbone=dict(type="ResNet", depth=18, strides=strides,
+                                                 out_indices=(2,), pool_type="none"),
+                                   train_cfg=None, test_cfg=cfg)
+        model.init_weights()
+        model.eval()
+        g = torch.Generator().manual_seed(5)
+        T = 5
+        base = torch.nn.functional.interpolate(torch.randn(1, 3, hw[0] // 4, hw[1] // 4, generator=g),
+                                               size=hw, mode="bilinear", align_corners=False)[0]
+        frames = [torch.roll(base, shifts=(t, 2 * t), dims=(1, 2)) + 0.02 * torch.randn(base.shape, generator=g)
+                  for t in range(T)]
+        rgbs = torch.stack(frames)[None]
+        qp = torch.tensor([[[0, 10., 12.], [0, 30., 20.], [1, 22., 9.], [0, 5., 25.], [2, 17., 17.]]])
+        P = qp.shape[1]
+        with torch.no_grad():
+            res = model(test_mode=True, rgbs=rgbs, query_points=qp,
+                        trajectories=torch.zeros(1, T, P, 2), visibilities=torch.zeros(1, T, P))
+            feats = model.extract_feat_test(rgbs[0])
+        out[f"{tag}_rgbs"] = rgbs.numpy()
+        out[f"{tag}_feats"] = feats.numpy().astype(np.float32)
+        out[f"{tag}_query_points"] = qp.numpy()
+        out[f"{tag}_traj_pred"] = res[2].numpy()
+        out[f"{tag}_query_points_remap"] = res[4].numpy()
+        out[f"{tag}_neighbor_range"] = nr
+        out[f"{tag}_precede_frames"] = 2
+        # img2coord on a propagated-looking map
+    maps = np.random.RandomState(3).rand(3, 4, 9, 11).astype(np.float32)
+    maps[1, 2] = 0
+    out["i2c_maps"] = maps
+    out["i2c_xy"] = trk.VanillaTracker.img2coord(None, maps, num_poses=4)
+    np.savez_compressed(os.path.join(OUT, "tracker.npz"), **out)
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = ref_loader.load_functions()
+    print("propagate:", gen_propagate(ref))
+    gen_masks(ref)
+    gen_c2f(ref)
+    gen_legacy(ref)
+    gen_tracker()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""The oracle restatement vs. the committed outputs of the genuine reference
+(tests/golden/*.npz, written by oracle/gen_golden.py).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+PROP = ["rand_small", "rand_nonmask1", "coh_dupframe0", "coh_c256", "tiny_fewcands"]
+
+
+@pytest.mark.parametrize("name", PROP)
+def test_propagate_port_matches_reference(golden_dir, name):
+    d = _load(golden_dir, f"prop_{name}.npz")
+    q, k, v = (torch.from_numpy(d[x]) for x in "qkv")
+    nr, topk, nml = int(d["neighbor_range"]), int(d["topk"]), int(d["non_mask_len"])
+    H, W = q.shape[2:]
+    mask = O.neighbor_mask(H, W, nr)
+    out = O.propagate_port(q, k, v, mask=mask, temperature=0.07, topk=topk, step=64, non_mask_len=nml)
+    assert torch.allclose(out, torch.from_numpy(d["out_v1"]), atol=2e-6, rtol=0)
+    out2 = O.propagate_port(q, k, v, radius=nr // 2, temperature=0.07, topk=topk, step=64)
+    assert torch.allclose(out2, torch.from_numpy(d["out_v2"]), atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("name", PROP)
+def test_propagate_exact_matches_reference(golden_dir, name):
+    d = _load(golden_dir, f"prop_{name}.npz")
+    q, k, v = (torch.from_numpy(d[x]) for x in "qkv")
+    nr, topk, nml = int(d["neighbor_range"]), int(d["topk"]), int(d["non_mask_len"])
+    T = k.shape[2]
+    ex = O.propagate_exact(q, k, v, radius=nr // 2, temperature=0.07, topk=topk,
+                           masked=[t >= nml for t in range(T)])
+    rep = O.compare_labels(d["out_v1"][0], ex["out"], ex["gap"], gap_eps=1e-4)
+    assert rep["max_abs_clear"] < 5e-6, rep
+    # ambiguous queries are rare and the only place the two may disagree
+    assert rep["n_ambiguous"] <= 0.02 * ex["gap"].numel() + 2, rep
+
+
+def test_masks_match_reference(golden_dir):
+    d = _load(golden_dir, "masks.npz")
+    for key in d.files:
+        mode, H, W, nr = key.split("_")
+        got = O.neighbor_mask(int(H), int(W), int(nr), mode).numpy()
+        assert (got == d[key]).all(), key
+
+
+def test_c2f_matches_reference(golden_dir):
+    d = _load(golden_dir, "c2f_small.npz")
+    t = {k: torch.from_numpy(d[k]) for k in ("q", "k", "qf", "kf", "v")}
+    H, W = t["q"].shape[2:]
+    mask = O.neighbor_mask(H, W, int(d["neighbor_range"]))
+    got = O.c2f_port(t["q"], t["k"], t["qf"], t["kf"], t["v"], mask, temperature=0.07,
+                     topk=int(d["topk"]), radius_fine=int(d["radius_fine"]))
+    assert torch.allclose(got["out"], torch.from_numpy(d["out"]), atol=5e-6, rtol=0)
+    got64 = O.c2f_port(t["q"], t["k"], t["qf"], t["kf"], t["v"], mask, temperature=0.07,
+                       topk=int(d["topk"]), radius_fine=int(d["radius_fine"]), dtype=torch.float64)
+    assert (got64["out"].float() - torch.from_numpy(d["out"])).abs().max() < 5e-5
+
+
+def test_img2coord_matches_reference(golden_dir):
+    d = _load(golden_dir, "tracker.npz")
+    got = O.img2coord_port(d["i2c_maps"])
+    assert np.allclose(got, d["i2c_xy"], atol=1e-12)
+    assert (got[:, 2, 1] == -1).all()
+
+
+@pytest.mark.parametrize("tag", ["s8", "s2"])
+def test_tracker_driver_matches_reference(golden_dir, tag):
+    """forward_test grouping + forward_test_main loop, from the genuine encoder's features."""
+    d = _load(golden_dir, "tracker.npz")
+    feats = torch.from_numpy(d[f"{tag}_feats"])
+    qp = d[f"{tag}_query_points"][0]
+    rgbs = d[f"{tag}_rgbs"]
+    T, (h, w) = rgbs.shape[1], rgbs.shape[3:]
+    cfg = dict(precede_frames=int(d[f"{tag}_precede_frames"]), topk=10, temperature=0.07,
+               neighbor_range=int(d[f"{tag}_neighbor_range"]), step=64, with_first=True,
+               with_first_neighbor=True)
+    pred = np.zeros((T, qp.shape[0], 2))
+    remap = np.zeros_like(qp)
+    col = 0
+    for t0, idx in O.group_by_query_frame(qp):
+        _, traj = O.track_clip_port(feats[t0:], torch.from_numpy(qp[idx, 1:]), (h, w), cfg)
+        pred[t0:, col:col + len(idx)] = traj
+        remap[col:col + len(idx)] = qp[idx]
+        col += len(idx)
+    assert np.allclose(remap, d[f"{tag}_query_points_remap"][0])
+    assert np.abs(pred - d[f"{tag}_traj_pred"][0]).max() < 1e-3
+
+
+def test_legacy_matches_reference(golden_dir):
+    d = _load(golden_dir, "legacy.npz")
+    a, b, img = (torch.from_numpy(d[k]) for k in ("a", "b", "img"))
+    aff = O.compute_affinity_port(a, b, temperature=0.07, softmax_dim=1)
+    assert torch.allclose(aff, torch.from_numpy(d["aff"]), atol=1e-6)
+    prop = O.propagate_legacy_port(img, aff, topk=4)
+    assert torch.allclose(prop, torch.from_numpy(d["prop"]), atol=1e-5)
+
+
+def test_sharding_and_collect_order():
+    # datasets/samplers/distributed_sampler.py:49-53 and apis/test.py:231-235
+    assert O.shard_indices(10, 1, 4) == [1, 5, 9]
+    assert O.shard_indices(10, 3, 4) == [3, 7, 1]
+    parts = [[f"r{r}i{i}" for i in O.shard_indices(10, r, 4)] for r in range(4)]
+    got = O.interleave_results(parts, 10)
+    assert got == [f"r{i % 4}i{i}" for i in range(10)]
+
+
+def test_memory_multiset_duplicates_frame0():
+    assert O.memory_frames(1, 5) == [0, 0]
+    assert O.memory_frames(3, 5) == [0, 0, 1, 2]
+    assert O.memory_frames(8, 5) == [0, 3, 4, 5, 6, 7]
+    assert O.memory_frames(3, 5, with_first=False) == [0, 1, 2]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+def test_live_reference_agrees_with_port():
+    """In the build container also execute the genuine function on fresh seeded inputs."""
+    from oracle import ref_loader
+    ref = ref_loader.load_functions()
+    g = torch.Generator().manual_seed(99)
+    q = torch.randn(1, 48, 11, 13, generator=g)
+    k = torch.randn(1, 48, 3, 11, 13, generator=g)
+    v = torch.rand(1, 4, 3, 11, 13, generator=g)
+    m = ref.spatial_neighbor(1, 11, 13, neighbor_range=8, device="cpu", dtype=torch.float32)
+    want = ref.masked_attention_efficient(q, k, v, m, temperature=0.07, topk=10, step=50)
+    got = O.propagate_port(q, k, v, mask=O.neighbor_mask(11, 13, 8), temperature=0.07, topk=10, step=50)
+    assert torch.allclose(got, want, atol=2e-6, rtol=0)

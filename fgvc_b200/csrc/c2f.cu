@@ -1,0 +1,162 @@
+// K2: coarse-to-fine propagation (local_attention.py:721-880).
+//
+// Coarse stage: K1 with K = 1 and one group per memory frame gives, for every coarse
+// query and memory frame, the arg-max key inside the radius mask (:804-837).
+// Fine stage (this file): one CTA per coarse query.  For every memory frame the
+// (2*rf+1)^2 window of the fine key map centred at scale*(ky,kx) is read straight from
+// the pixel-major fine bank -- the R^2-fold F.unfold blow-up of the reference (:790-793)
+// never exists.  One warp per candidate: lanes stride the contiguous channel dimension
+// (coalesced 128-bit loads), butterfly-reduce the dot product, and every lane keeps the
+// same sorted top-K so there is no divergence.  Out-of-map candidates compete with
+// affinity 0 and value 0 exactly as the zero padding of the reference does.
+#include "common.cuh"
+
+namespace fgvc {
+
+template <int K>
+__global__ void __launch_bounds__(256)
+c2f_fine_kernel(const float* __restrict__ fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
+                fgvc_job job, const int32_t* __restrict__ mem_feat, const int32_t* __restrict__ mem_label,
+                const int32_t* __restrict__ best_idx, int rf, int k_out, float temperature,
+                const float* __restrict__ fine_lab, int Lp, float* __restrict__ out) {
+  extern __shared__ __align__(16) float qf[];  // [Cf]
+  __shared__ float lv[8][K];
+  __shared__ int li[8][K];
+  __shared__ float sw[K];
+  __shared__ int srow[K];
+  const int q = blockIdx.x;
+  const int qy = q / Wc, qx = q - qy * Wc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nf = Hf * Wf, nc = Hc * Wc;
+  const int64_t slot_floats = feat_slot_floats(nf, Cf);
+  {
+    const float* hi = fine_bank + (int64_t)job.q_slot * slot_floats + (int64_t)((qy * scale) * Wf + qx * scale) * Cf;
+    const float* lo = hi + (int64_t)nf * Cf;
+    for (int c = tid; c < Cf; c += 256) qf[c] = __ldg(hi + c) + __ldg(lo + c);
+  }
+  __syncthreads();
+  const int R = 2 * rf + 1;
+  const int n_mem = job.mem_end - job.mem_begin;
+  TopK<K> top;
+  top.init();
+  const int c4n = Cf / 4;
+  for (int t = 0; t < n_mem; ++t) {
+    const int slot = __ldg(mem_feat + job.mem_begin + t) & ~FGVC_MEM_UNMASKED;
+    const int b = max(__ldg(best_idx + (int64_t)t * nc + q), 0) % nc;   // coarse arg-max key pixel
+    const int cy = (b / Wc) * scale, cx = (b % Wc) * scale;
+    const float* hi = fine_bank + (int64_t)slot * slot_floats;
+    const float* lo = hi + (int64_t)nf * Cf;
+    for (int w = warp; w < R * R; w += 8) {
+      int dy = w / R - rf, dx = w % R - rf;
+      int y = cy + dy, x = cx + dx;
+      float dot = 0.f;
+      if (y >= 0 && y < Hf && x >= 0 && x < Wf) {
+        const float4* h4 = reinterpret_cast<const float4*>(hi + (int64_t)(y * Wf + x) * Cf);
+        const float4* l4 = reinterpret_cast<const float4*>(lo + (int64_t)(y * Wf + x) * Cf);
+        for (int c = lane; c < c4n; c += 32) {
+          float4 a = __ldg(h4 + c), bb = __ldg(l4 + c);
+          float4 qq = *reinterpret_cast<const float4*>(qf + 4 * c);
+          dot = fmaf(a.x + bb.x, qq.x, dot); dot = fmaf(a.y + bb.y, qq.y, dot);
+          dot = fmaf(a.z + bb.z, qq.z, dot); dot = fmaf(a.w + bb.w, qq.w, dot);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      }
+      // candidate id = t * R^2 + w; padded candidates carry affinity 0
+      if (dot > top.thr()) top.push(dot, t * R * R + w);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lv[warp][i] = top.v[i]; li[warp][i] = top.id[i]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    TopK<K> m;
+    m.init();
+    for (int w = 0; w < 8; ++w)
+      for (int i = 0; i < K; ++i)
+        if (li[w][i] >= 0 && lv[w][i] > m.thr()) m.push(lv[w][i], li[w][i]);
+    float a[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) a[i] = __fdiv_rn(m.v[i], temperature);
+    float mx = a[0], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      a[i] = (i < k_out && m.id[i] >= 0) ? expf(a[i] - mx) : 0.f;
+      sum += a[i];
+    }
+    for (int i = 0; i < K; ++i) {
+      bool ok = i < k_out && m.id[i] >= 0;
+      float w = ok ? __fdiv_rn(a[i], sum) : 0.f;
+      int row = -1;
+      if (ok) {
+        int t = m.id[i] / (R * R), wdx = m.id[i] - t * R * R;
+        int b = max(__ldg(best_idx + (int64_t)t * nc + q), 0) % nc;
+        int y = (b / Wc) * scale + wdx / R - rf, x = (b % Wc) * scale + wdx % R - rf;
+        if (y >= 0 && y < Hf && x >= 0 && x < Wf)
+          row = __ldg(mem_label + job.mem_begin + t) * nf + y * Wf + x;
+      }
+      sw[i] = w;
+      srow[i] = row;   // row < 0: zero-padded candidate, contributes value 0
+    }
+  }
+  __syncthreads();
+  const int l4n = Lp / 4;
+  const float4* src = reinterpret_cast<const float4*>(fine_lab);
+  float4* dst = reinterpret_cast<float4*>(out) + (int64_t)q * l4n;
+  for (int c = tid; c < l4n; c += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (srow[j] >= 0 && sw[j] != 0.f) {
+        float4 v = __ldg(src + (int64_t)srow[j] * l4n + c);
+        acc.x = fmaf(sw[j], v.x, acc.x); acc.y = fmaf(sw[j], v.y, acc.y);
+        acc.z = fmaf(sw[j], v.z, acc.z); acc.w = fmaf(sw[j], v.w, acc.w);
+      }
+    }
+    dst[c] = acc;
+  }
+}
+
+template <int K>
+static int launch_fine(const float* fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
+                       const fgvc_job& job, const int32_t* mem_feat, const int32_t* mem_label,
+                       const int32_t* best, int rf, int k_out, float temperature, const float* fine_lab, int Lp,
+                       float* out, cudaStream_t st) {
+  c2f_fine_kernel<K><<<Hc * Wc, 256, Cf * sizeof(float), st>>>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, job,
+                                                               mem_feat, mem_label, best, rf, k_out, temperature,
+                                                               fine_lab, Lp, out);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+}  // namespace fgvc
+
+using namespace fgvc;
+
+extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t Hc, int32_t Wc, int32_t C,
+                                  const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
+                                  const fgvc_job* job_dev, const fgvc_job* job_host, const int32_t* mem_feat_slot,
+                                  const int32_t* mem_label_slot, int32_t radius, int32_t mask_mode,
+                                  int32_t radius_fine, int32_t K, float temperature, const float* fine_lab_bank,
+                                  int32_t Lp, float* out, float* scratch_val, int32_t* scratch_idx, int32_t engine,
+                                  void* stream) {
+  FGVC_CHECK_ARG(coarse_bank && fine_bank && job_dev && job_host && mem_feat_slot && mem_label_slot &&
+                     fine_lab_bank && out && scratch_val && scratch_idx, "fgvc_c2f_propagate: null pointer");
+  FGVC_CHECK_ARG(Hc > 0 && Wc > 0 && Hf % Hc == 0 && Hf / Hc >= 1 && Wf >= Wc * (Hf / Hc) - (Hf / Hc) + 1,
+                 "fgvc_c2f_propagate: fine map %dx%d is not a multiple of the coarse map %dx%d", Hf, Wf, Hc, Wc);
+  FGVC_CHECK_ARG(K >= 1 && K <= 16, "fgvc_c2f_propagate: topk=%d not in [1,16]", K);
+  FGVC_CHECK_ARG(Cf % 4 == 0 && Lp % 4 == 0 && radius_fine >= 0 && temperature > 0, "fgvc_c2f_propagate: bad sizes");
+  const int n_mem = job_host->mem_end - job_host->mem_begin;
+  FGVC_CHECK_ARG(n_mem >= 1 && n_mem <= 64, "fgvc_c2f_propagate: memory length %d not in [1,64]", n_mem);
+  // coarse stage: top-1 per memory frame == groups = n_mem
+  int rc = fgvc_affinity_topk(coarse_bank, Hc, Wc, C, job_dev, 1, mem_feat_slot, radius, mask_mode, 1, n_mem,
+                              scratch_val, scratch_idx, engine, stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int scale = Hf / Hc;
+  if (K <= 4) return launch_fine<4>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
+  if (K <= 10) return launch_fine<10>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
+  return launch_fine<16>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
+}

@@ -1,0 +1,75 @@
+// extern "C" entry points that are pure plumbing: error state, engine dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fgvc {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace fgvc
+
+using namespace fgvc;
+
+extern "C" const char* fgvc_last_error(void) { return g_err; }
+extern "C" int fgvc_version(void) { return FGVC_VERSION; }
+extern "C" int64_t fgvc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int fgvc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int fgvc_tc_supported(int32_t H, int32_t W, int32_t C, int32_t K) { return tc_supported(H, W, C, K) ? 1 : 0; }
+
+extern "C" int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K) {
+  return (int64_t)n_jobs * groups * n_query * K * 4;
+}
+
+static int pick_engine(int engine, int H, int W, int C, int K, bool* use_tc) {
+  bool ok = tc_supported(H, W, C, K);
+  if (engine == FGVC_ENGINE_TCGEN05) {
+    FGVC_CHECK_ARG(ok, "tcgen05 engine needs C %% 32 == 0, C <= 512 and K <= 16 (C=%d K=%d)", C, K);
+    *use_tc = true;
+  } else if (engine == FGVC_ENGINE_SIMT) {
+    *use_tc = false;
+  } else {
+    FGVC_CHECK_ARG(engine == FGVC_ENGINE_AUTO, "unknown engine %d", engine);
+    *use_tc = ok;
+  }
+  return FGVC_OK;
+}
+
+extern "C" int fgvc_affinity_topk(const float* feat_bank, int32_t H, int32_t W, int32_t C, const fgvc_job* jobs,
+                                  int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius, int32_t mask_mode,
+                                  int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx, int32_t engine,
+                                  void* stream) {
+  FGVC_CHECK_ARG(feat_bank && jobs && mem_feat_slot && topk_val && topk_idx, "fgvc_affinity_topk: null pointer");
+  FGVC_CHECK_ARG(H > 0 && W > 0 && C > 0 && n_jobs > 0, "fgvc_affinity_topk: bad shape");
+  FGVC_CHECK_ARG(K >= 1 && K <= 16, "fgvc_affinity_topk: topk=%d not in [1,16]", K);
+  FGVC_CHECK_ARG(groups >= 1 && groups <= 64, "fgvc_affinity_topk: groups=%d not in [1,64]", groups);
+  FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk: radius=%d must be >= 1", radius);
+  FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk: bad mask mode");
+  bool use_tc = false;
+  int rc = pick_engine(engine, H, W, C, K, &use_tc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc)
+    return launch_affinity_topk_tc(feat_bank, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
+                                   topk_val, topk_idx, st);
+  return launch_affinity_topk_simt(feat_bank, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
+                                   topk_val, topk_idx, st);
+}

@@ -1,0 +1,96 @@
+// Shared helpers for the fgvc_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/fgvc_b200.h"
+
+namespace fgvc {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define FGVC_CHECK_ARG(cond, ...)                   \
+  do {                                              \
+    if (!(cond)) {                                  \
+      fgvc::set_error(__VA_ARGS__);                 \
+      return FGVC_ERR_INVALID;                      \
+    }                                               \
+  } while (0)
+
+#define FGVC_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      fgvc::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,  \
+                      __LINE__);                                                          \
+      return FGVC_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define FGVC_LAUNCH_CHECK()                 \
+  do {                                      \
+    fgvc::g_launches.fetch_add(1);          \
+    FGVC_CUDA(cudaGetLastError());          \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// size in floats of one feature-bank slot: [2][n_pix][C]
+__host__ __device__ inline int64_t feat_slot_floats(int n_pix, int C) { return 2ll * n_pix * C; }
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- sorted (descending) top-K list held in registers -------------------------------
+template <int K>
+struct TopK {
+  float v[K];
+  int id[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      v[i] = -INFINITY;
+      id[i] = -1;
+    }
+  }
+  __device__ __forceinline__ float thr() const { return v[K - 1]; }
+  // caller guarantees x > thr()
+  __device__ __forceinline__ void push(float x, int i) {
+    v[K - 1] = x;
+    id[K - 1] = i;
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+      if (v[j] > v[j - 1]) {
+        float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+        int ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+      }
+    }
+  }
+};
+
+// in-mask test shared by every kernel (affinity_utils.py:85-112):
+// circle: dy^2 + dx^2 < r^2 (strict); square: |dy| <= r and |dx| <= r
+__device__ __forceinline__ bool in_mask(int dy, int dx, int r, int mode) {
+  if (mode == FGVC_MASK_CIRCLE) return dy * dy + dx * dx < r * r;
+  return (dy <= r) && (dy >= -r) && (dx <= r) && (dx >= -r);
+}
+// largest |d| that can be in-mask
+__host__ __device__ inline int mask_reach(int r, int mode) { return mode == FGVC_MASK_CIRCLE ? r - 1 : r; }
+
+// host launchers implemented in the .cu files -------------------------------------------
+int launch_affinity_topk_simt(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+                              const int32_t* mem_feat, int radius, int mode, int K, int groups,
+                              float* tv, int32_t* ti, cudaStream_t st);
+int launch_affinity_topk_tc(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+                            const int32_t* mem_feat, int radius, int mode, int K, int groups,
+                            float* tv, int32_t* ti, cudaStream_t st);
+bool tc_supported(int H, int W, int C, int K);
+
+}  // namespace fgvc

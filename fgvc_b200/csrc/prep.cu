@@ -1,0 +1,156 @@
+// K0: feature preparation and label layout kernels (HBM-bound, coalesced both ways).
+#include "common.cuh"
+
+namespace fgvc {
+
+// One block = 32 consecutive pixels x all C channels of one frame.
+// Read: for each channel a warp reads 32 consecutive pixels (128 B, coalesced).
+// Write: for each pixel consecutive threads write consecutive channels (coalesced).
+// smem tile[C][33] breaks the transpose bank conflicts.
+__global__ void __launch_bounds__(256)
+prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_t chan_stride, int C,
+                     int n_pix, int normalize, float* __restrict__ bank, int first_slot) {
+  extern __shared__ float tile[];  // [C][33] + norm[32]
+  float* inv = tile + C * 33;
+  const int frame = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* s = src + frame * frame_stride;
+  for (int c = warp; c < C; c += 8) {
+    int p = p0 + lane;
+    tile[c * 33 + lane] = (p < n_pix) ? __ldg(s + c * chan_stride + p) : 0.f;
+  }
+  __syncthreads();
+  // per-pixel L2 norm over C: warp w handles pixels w, w+8, ...
+  for (int pp = warp; pp < 32; pp += 8) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float x = tile[c * 33 + pp];
+      acc = fmaf(x, x, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) inv[pp] = normalize ? fmaxf(sqrtf(acc), 1e-12f) : 1.f;
+  }
+  __syncthreads();
+  float* hi = bank + (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
+  float* lo = hi + (int64_t)n_pix * C;
+  for (int i = threadIdx.x; i < 32 * C; i += 256) {
+    int pp = i / C, c = i - pp * C;
+    int p = p0 + pp;
+    if (p < n_pix) {
+      float x = __fdiv_rn(tile[c * 33 + pp], inv[pp]);
+      float h = tf32_round(x);
+      hi[(int64_t)p * C + c] = h;
+      lo[(int64_t)p * C + c] = x - h;
+    }
+  }
+}
+
+// NCHW [L][n_pix] -> pixel-major [n_pix][Lp] (pad channels zero-filled); 32x32 tiles
+__global__ void __launch_bounds__(256)
+labels_to_pixmajor_kernel(const float* __restrict__ src, int64_t chan_stride, int L, int n_pix,
+                          float* __restrict__ dst, int Lp) {
+  __shared__ float t[32][33];
+  const int p0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    int l = l0 + j, p = p0 + tx;
+    t[j][tx] = (l < L && p < n_pix) ? __ldg(src + l * chan_stride + p) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, l = l0 + tx;
+    if (p < n_pix && l < Lp) dst[(int64_t)p * Lp + l] = t[tx][j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+labels_to_nchw_kernel(const float* __restrict__ src, int Lp, int L, int n_pix, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int p0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, l = l0 + tx;
+    t[j][tx] = (p < n_pix && l < Lp) ? __ldg(src + (int64_t)p * Lp + l) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int l = l0 + j, p = p0 + tx;
+    if (l < L && p < n_pix) dst[(int64_t)l * n_pix + p] = t[tx][j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gaussian_labels_kernel(const float* __restrict__ pts, int P, int H, int W, int stride, float denom,
+                       float* __restrict__ dst, int Lp) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int64_t total = (int64_t)H * W * Lp;
+  if (i >= total) return;
+  int p = (int)(i % Lp);
+  int pix = (int)(i / Lp);
+  float v = 0.f;
+  if (p < P) {
+    float x = (float)((pix % W) * stride), y = (float)((pix / W) * stride);
+    float dx = x - __ldg(pts + 2 * p), dy = y - __ldg(pts + 2 * p + 1);
+    // reference: exp(-((gx-cx)**2 + (gy-cy)**2) / (2*sigma**2))
+    v = expf(__fdiv_rn(-(dx * dx + dy * dy), denom));
+  }
+  dst[i] = v;
+}
+
+}  // namespace fgvc
+
+using namespace fgvc;
+
+extern "C" int fgvc_prep_features(const float* src, int64_t src_frame_stride, int64_t src_chan_stride,
+                                  int32_t n_frames, int32_t C, int32_t H, int32_t W, int32_t normalize,
+                                  float* feat_bank, int32_t first_slot, void* stream) {
+  FGVC_CHECK_ARG(src && feat_bank, "fgvc_prep_features: null pointer");
+  FGVC_CHECK_ARG(n_frames > 0 && C > 0 && H > 0 && W > 0, "fgvc_prep_features: bad shape");
+  FGVC_CHECK_ARG(C % 4 == 0 && C <= 1024, "fgvc_prep_features: C=%d must be a multiple of 4, <= 1024", C);
+  int n_pix = H * W;
+  size_t smem = (size_t)(C * 33 + 32) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(n_pix, 32), n_frames);
+  prep_features_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_frame_stride, src_chan_stride, C,
+                                                                  n_pix, normalize, feat_bank, first_slot);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+extern "C" int fgvc_labels_to_pixmajor(const float* src, int64_t src_chan_stride, int32_t L, int32_t n_pix,
+                                       float* lab_bank, int32_t slot, int32_t Lp, void* stream) {
+  FGVC_CHECK_ARG(src && lab_bank && L > 0 && n_pix > 0 && Lp >= L && Lp % 4 == 0,
+                 "fgvc_labels_to_pixmajor: bad arguments (L=%d Lp=%d)", L, Lp);
+  dim3 grid(cdiv(n_pix, 32), cdiv(Lp, 32));
+  labels_to_pixmajor_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_chan_stride, L, n_pix,
+                                                                    lab_bank + (int64_t)slot * n_pix * Lp, Lp);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+extern "C" int fgvc_labels_to_nchw(const float* lab_bank, int32_t slot, int32_t Lp, int32_t L, int32_t n_pix,
+                                   float* dst, void* stream) {
+  FGVC_CHECK_ARG(dst && lab_bank && L > 0 && n_pix > 0 && Lp >= L, "fgvc_labels_to_nchw: bad arguments");
+  dim3 grid(cdiv(n_pix, 32), cdiv(L, 32));
+  labels_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lab_bank + (int64_t)slot * n_pix * Lp, Lp, L,
+                                                                n_pix, dst);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+extern "C" int fgvc_gaussian_labels(const float* points_xy, int32_t P, int32_t H, int32_t W, int32_t stride,
+                                    float sigma, float* lab_bank, int32_t slot, int32_t Lp, void* stream) {
+  FGVC_CHECK_ARG(points_xy && lab_bank && P > 0 && Lp >= P && Lp % 4 == 0 && sigma > 0,
+                 "fgvc_gaussian_labels: bad arguments");
+  int64_t total = (int64_t)H * W * Lp;
+  gaussian_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      points_xy, P, H, W, stride, 2.f * sigma * sigma, lab_bank + (int64_t)slot * H * W * Lp, Lp);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}

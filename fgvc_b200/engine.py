@@ -1,0 +1,204 @@
+"""Device-side state of the propagation path: feature bank, label bank, job tables, and
+thin wrappers that enqueue the CUDA kernels through the C ABI (fgvc_b200/_lib.py).
+
+Vocabulary follows the reference (``feat_bank`` / ``seg_bank`` of
+mmpt/models/trackers/vanilla_tracker.py:318-394): a *slot* holds one frame.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Job, call, ptr, stream_ptr
+
+NUM_SMS = 148
+
+
+def pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class FeatureBank:
+    """feat[slot][2][H*W][C]: L2-normalised, pixel-major, TF32 hi/lo split (K0 output)."""
+
+    def __init__(self, n_slots, C, H, W, device):
+        _lib.require_cuda()
+        self.n_slots, self.C, self.H, self.W = n_slots, C, H, W
+        self.buf = torch.empty(n_slots, 2, H * W, C, dtype=torch.float32, device=device)
+
+    def load(self, src, first_slot, n_frames, frame_stride, chan_stride, normalize=True):
+        """src: fp32 CUDA tensor; frame f / channel c / pixel p at
+        ``src.data_ptr + 4*(f*frame_stride + c*chan_stride + p)``."""
+        assert src.is_cuda and src.dtype == torch.float32
+        assert 0 <= first_slot and first_slot + n_frames <= self.n_slots
+        call("fgvc_prep_features", ptr(src), frame_stride, chan_stride, n_frames, self.C, self.H, self.W,
+             int(bool(normalize)), ptr(self.buf), first_slot, stream_ptr())
+
+    def load_frames(self, feats, first_slot=0, normalize=True):
+        """feats [n,C,H,W] contiguous."""
+        feats = feats.contiguous()
+        n, C, H, W = feats.shape
+        assert (C, H, W) == (self.C, self.H, self.W)
+        self.load(feats, first_slot, n, C * H * W, H * W, normalize)
+
+
+class LabelBank:
+    """lab[slot][H*W][Lp], Lp = L padded to a multiple of 4."""
+
+    def __init__(self, n_slots, L, H, W, device):
+        _lib.require_cuda()
+        self.n_slots, self.L, self.Lp, self.H, self.W = n_slots, L, pad4(L), H, W
+        self.buf = torch.empty(n_slots, H * W, self.Lp, dtype=torch.float32, device=device)
+
+    def put_nchw(self, src, slot, chan_stride=None):
+        """src: [L,H,W] view whose pixels are contiguous; chan_stride in floats."""
+        assert src.is_cuda and src.dtype == torch.float32
+        if chan_stride is None:
+            src = src.contiguous()
+            chan_stride = self.H * self.W
+        call("fgvc_labels_to_pixmajor", ptr(src), chan_stride, self.L, self.H * self.W, ptr(self.buf), slot,
+             self.Lp, stream_ptr())
+
+    def get_nchw(self, slot, out=None):
+        if out is None:
+            out = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.buf.device)
+        call("fgvc_labels_to_nchw", ptr(self.buf), slot, self.Lp, self.L, self.H * self.W, ptr(out), stream_ptr())
+        return out
+
+    def put_gaussians(self, points_xy, slot, stride, sigma=6.0):
+        """draw_gaussion_map_online at feature resolution (vanilla_tracker.py:204-221)."""
+        pts = points_xy.to(device=self.buf.device, dtype=torch.float32).contiguous()
+        assert pts.shape == (self.L, 2)
+        call("fgvc_gaussian_labels", ptr(pts), self.L, self.H, self.W, int(stride), float(sigma), ptr(self.buf),
+             slot, self.Lp, stream_ptr())
+
+
+class JobTable:
+    """Propagation jobs: (query slot, memory list, output slot).  Host lists -> device int32."""
+
+    def __init__(self):
+        self.jobs, self.mem_feat, self.mem_label = [], [], []
+        self._dev = None
+
+    def add(self, q_slot, mem_feat_slots, mem_label_slots, out_slot, unmasked=0):
+        """``unmasked``: number of leading memory entries without the radius mask
+        (``non_mask_len``, local_attention.py:347)."""
+        assert len(mem_feat_slots) == len(mem_label_slots) >= 1
+        b = len(self.mem_feat)
+        for i, s in enumerate(mem_feat_slots):
+            self.mem_feat.append(int(s) | (_lib.MEM_UNMASKED if i < unmasked else 0))
+        self.mem_label.extend(int(s) for s in mem_label_slots)
+        self.jobs.append((int(q_slot), b, b + len(mem_feat_slots), int(out_slot)))
+        self._dev = None
+        return len(self.jobs) - 1
+
+    def __len__(self):
+        return len(self.jobs)
+
+    @property
+    def max_mem(self):
+        return max(j[2] - j[1] for j in self.jobs)
+
+    def device(self, device):
+        if self._dev is None or self._dev[0].device != torch.device(device):
+            j = torch.tensor(self.jobs, dtype=torch.int32).reshape(-1, 4).to(device)
+            mf = torch.tensor(self.mem_feat, dtype=torch.int32).to(device)
+            ml = torch.tensor(self.mem_label, dtype=torch.int32).to(device)
+            self._dev = (j, mf, ml)
+        return self._dev
+
+    def host_job(self, i):
+        return Job(*self.jobs[i])
+
+
+def pick_groups(n_jobs, H, W, max_mem, tile=64):
+    """Split memory lists so that a short job list still fills 148 SMs about twice."""
+    ctas = n_jobs * ((H * W + tile - 1) // tile)
+    g = (2 * NUM_SMS + ctas - 1) // ctas
+    return int(max(1, min(g, max_mem, 64)))
+
+
+class TopKLists:
+    def __init__(self, n_jobs, groups, n_query, K, device):
+        self.n_jobs, self.groups, self.n_query, self.K = n_jobs, groups, n_query, K
+        self.val = torch.empty(n_jobs, groups, n_query, K, dtype=torch.float32, device=device)
+        self.idx = torch.empty(n_jobs, groups, n_query, K, dtype=torch.int32, device=device)
+
+
+def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None):
+    """K1 over every job of ``table`` in one launch."""
+    dev = bank.buf.device
+    jobs, mem_feat, _ = table.device(dev)
+    if groups is None:
+        groups = pick_groups(len(table), bank.H, bank.W, table.max_mem)
+    if lists is None:
+        lists = TopKLists(len(table), groups, bank.H * bank.W, K, dev)
+    assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table)
+    mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
+    call("fgvc_affinity_topk", ptr(bank.buf), bank.H, bank.W, bank.C, ptr(jobs), len(table), ptr(mem_feat),
+         int(radius), mode, int(K), int(groups), ptr(lists.val), ptr(lists.idx), int(engine), stream_ptr())
+    return lists
+
+
+def gather_labels(lists, table, job_begin, job_end, labels, temperature):
+    """K1b for jobs [job_begin, job_end): writes each job's out_slot of ``labels``."""
+    dev = labels.buf.device
+    jobs, _, mem_label = table.device(dev)
+    call("fgvc_gather_labels", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups, ptr(jobs), int(job_begin),
+         int(job_end), ptr(mem_label), labels.H * labels.W, float(temperature), ptr(labels.buf), labels.Lp,
+         stream_ptr())
+
+
+def heatmap_coords(maps, out_hw, topk=5):
+    """K3: maps [n,H,W] fp32 CUDA -> [n,2] (x,y) after bilinear up-sampling to out_hw."""
+    maps = maps.contiguous()
+    n, H, W = maps.shape
+    out = torch.empty(n, 2, dtype=torch.float32, device=maps.device)
+    call("fgvc_heatmap_coords", ptr(maps), n, H, W, int(out_hw[0]), int(out_hw[1]), int(topk), ptr(out), stream_ptr())
+    return out
+
+
+def gaussian_coords(points_xy, out_hw, sigma=6.0, topk=5):
+    pts = points_xy.to(dtype=torch.float32).contiguous()
+    out = torch.empty(pts.shape[0], 2, dtype=torch.float32, device=pts.device)
+    call("fgvc_gaussian_coords", ptr(pts), pts.shape[0], int(out_hw[0]), int(out_hw[1]), float(sigma), int(topk),
+         ptr(out), stream_ptr())
+    return out
+
+
+def decode_masks(maps, out_hw):
+    """VOS-style decode: maps [L,H,W] -> uint8 [h,w] (vanilla_tracker.py:769-798)."""
+    maps = maps.contiguous()
+    L, H, W = maps.shape
+    scratch = torch.empty(2 * L, dtype=torch.float32, device=maps.device)
+    out = torch.empty(out_hw[0], out_hw[1], dtype=torch.uint8, device=maps.device)
+    call("fgvc_decode_masks", ptr(maps), L, H, W, int(out_hw[0]), int(out_hw[1]), ptr(scratch), ptr(out), stream_ptr())
+    return out
+
+
+def memory_frames(t, precede_frames, with_first=True, first=0):
+    """Memory multiset of query frame t for a clip starting at ``first``
+    (vanilla_tracker.py:346-362): the first frame is prepended even when the window
+    already holds it."""
+    win = list(range(max(first, t - precede_frames), t))
+    return ([first] + win) if with_first else win
+
+
+def c2f_propagate(coarse, fine, table, job_index, fine_labels, radius, radius_fine, K, temperature,
+                  mask_mode="circle", engine=_lib.ENGINE_AUTO):
+    dev = coarse.buf.device
+    jobs, mem_feat, mem_label = table.device(dev)
+    hj = table.host_job(job_index)
+    n_mem = hj.mem_end - hj.mem_begin
+    nq = coarse.H * coarse.W
+    out = torch.empty(nq, fine_labels.Lp, dtype=torch.float32, device=dev)
+    sv = torch.empty(n_mem * nq, dtype=torch.float32, device=dev)
+    si = torch.empty(n_mem * nq, dtype=torch.int32, device=dev)
+    mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
+    jptr = ctypes.c_void_p(jobs.data_ptr() + 16 * job_index)
+    call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
+         jptr, ctypes.byref(hj), ptr(mem_feat), ptr(mem_label), int(radius), mode, int(radius_fine), int(K),
+         float(temperature), ptr(fine_labels.buf), fine_labels.Lp, ptr(out), ptr(sv), ptr(si), int(engine),
+         stream_ptr())
+    return out

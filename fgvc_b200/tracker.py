@@ -1,0 +1,198 @@
+"""Drop-in test-time tracker: same constructor and ``forward_test`` contract as the
+reference's ``VanillaTracker`` (mmpt/models/trackers/vanilla_tracker.py:75-412,
+``BaseModel.forward`` mmpt/models/trackers/base.py:44-60), label propagation on the
+B200 kernels.
+
+What changes relative to the reference loop (results identical, see tests):
+  * the clip is encoded ONCE for all ``with_first`` groups and the features stay in HBM
+    (reference: re-encodes per group and parks features on the CPU, :133-153, :262-284);
+  * affinity + mask + top-k of EVERY (group, frame) job is one kernel launch -- it does
+    not depend on the propagated labels; only the cheap gather is
+    sequential in time;
+  * heat-maps are never up-sampled into a [T,P,h,w] tensor nor shipped to the host:
+    K3 fuses the bilinear up-sampling with the top-5 soft-argmax (:396-406, :172-191).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, engine
+from .encoder import build_backbone
+from .engine import FeatureBank, JobTable, LabelBank
+
+
+class _Cfg(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class VanillaTracker(nn.Module):
+    """Pixel tracker; ``eval_arc='B200VanillaTracker'`` selects it in tools/test.py when
+    registered in mmpt's MODELS registry."""
+
+    def __init__(self, backbone, head=None, train_cfg=None, test_cfg=None, init_cfg=None):
+        super().__init__()
+        self.backbone = build_backbone(backbone)
+        self.head = head
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg if hasattr(test_cfg, "get") and hasattr(test_cfg, "precede_frames") \
+            else _Cfg(test_cfg or {})
+        self.stride_sample = self.test_cfg.get("stride_sample", False)
+        self.engine_id = self.test_cfg.get("engine", _lib.ENGINE_AUTO)
+        self.register_buffer("iteration", torch.tensor(0, dtype=torch.float))
+
+    def init_weights(self):
+        if hasattr(self.backbone, "init_weights"):
+            self.backbone.init_weights()
+
+    # ------------------------------------------------------------------ BaseModel.forward
+    def forward(self, test_mode=False, **kwargs):
+        if test_mode:
+            return self.forward_test(**kwargs)
+        return self.forward_train(**kwargs)
+
+    def forward_train(self, imgs, labels=None):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------- encoder
+    def extract_feat(self, imgs):
+        x = self.backbone(imgs)
+        if self.stride_sample:
+            x = x[:, :, ::self.stride_sample, ::self.stride_sample]
+        return x
+
+    @torch.no_grad()
+    def get_feats(self, frames):
+        """frames [T,3,h,w] -> [T,C,Hf,Wf] on the device, in chunks of ``batch_step``
+        (vanilla_tracker.py:133-153 without the round trip through host memory)."""
+        step = self.test_cfg.get("batch_step", 5)
+        outs = []
+        for s in range(0, frames.shape[0], step):
+            f = self.extract_feat(frames[s:s + step])
+            if isinstance(f, (tuple, list)):
+                f = f[0]
+            outs.append(f.float())
+        return torch.cat(outs, dim=0)
+
+    # --------------------------------------------------------------------- propagation
+    @torch.no_grad()
+    def propagate_points(self, feats, groups, image_hw):
+        """feats [T,C,Hf,Wf] (CUDA); groups: list of (t0, points_xy [P',2]).
+        Returns list of [T,P',2] float64 CUDA tensors (zeros before t0)."""
+        cfg = self.test_cfg
+        T, C, Hf, Wf = feats.shape
+        h, w = image_hw
+        dev = feats.device
+        stride = h // Hf
+        precede = cfg.precede_frames
+        with_first_mem = cfg.get("with_first", True)
+        v1 = cfg.get("test_mode", "v1") == "v1"
+        nr = cfg.get("neighbor_range", None)
+        if nr is None and not v1:
+            raise TypeError("test_mode v2 needs neighbor_range (the reference computes neighbor_range//2)")
+        unmasked_first = 0 if (cfg.get("with_first_neighbor", True) or not v1) else 1
+        if cfg.get("sim_mode", "dot_product") != "dot_product":
+            raise NotImplementedError("sim_mode='l2-distance' is not built")
+
+        bank = FeatureBank(T, C, Hf, Wf, dev)
+        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
+
+        table = JobTable()
+        spans = []   # per group: (first job, t0)
+        for t0, _ in groups:
+            spans.append((len(table), t0))
+            for t in range(t0 + 1, T):
+                mem = engine.memory_frames(t, precede, with_first_mem, first=t0)
+                table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
+        outs = []
+        if len(table) == 0:
+            lists = None
+        else:
+            lists = engine.affinity_topk(bank, table, (nr // 2) if nr is not None else 1, cfg.topk,
+                                         cfg.get("mask_mode", "circle"), engine=self.engine_id)
+        for (j0, t0), (_, pts) in zip(spans, groups):
+            P = pts.shape[0]
+            pts = pts.to(device=dev, dtype=torch.float32)
+            labels = LabelBank(T, P, Hf, Wf, dev)
+            labels.put_gaussians(pts, t0, stride)
+            traj = torch.zeros(T, P, 2, dtype=torch.float64, device=dev)
+            traj[t0] = engine.gaussian_coords(pts, (h, w)).double()
+            for t in range(t0 + 1, T):
+                j = j0 + (t - t0 - 1)
+                engine.gather_labels(lists, table, j, j + 1, labels, cfg.temperature)
+                traj[t] = engine.heatmap_coords(labels.get_nchw(t), (h, w)).double()
+            outs.append(traj)
+        return outs
+
+    def forward_test(self, rgbs, query_points, trajectories, visibilities, save_image=False, save_path=None,
+                     iteration=None):
+        """rgbs [1,T,3,h,w]; query_points [1,P,3] (t,x,y); trajectories [1,T,P,2];
+        visibilities [1,T,P].  Returns the reference's 5-tuple
+        (traj_gt, vis_gt, traj_pred, vis_pred, query_points), re-ordered by query frame
+        when ``test_cfg.with_first`` is set (vanilla_tracker.py:227-303)."""
+        _lib.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rgbs, query_points = rgbs.to(dev), query_points.to(dev)
+        trajectories, visibilities = trajectories.to(dev), visibilities.to(dev)
+        assert rgbs.shape[0] == 1
+        B, T = rgbs.shape[:2]
+        h, w = rgbs.shape[-2:]
+        feats = self.get_feats(rgbs[0])
+        if not self.test_cfg.get("with_first", False):
+            traj = self.propagate_points(feats, [(0, query_points[0, :, 1:])], (h, w))[0]
+            return trajectories, visibilities, traj[None], torch.zeros_like(visibilities), query_points
+        qt = query_points[0, :, 0]
+        ts = torch.unique(qt).tolist()
+        order = [torch.nonzero(qt == t).flatten() for t in ts]
+        groups = [(int(t), query_points[0, idx, 1:]) for t, idx in zip(ts, order)]
+        trajs = self.propagate_points(feats, groups, (h, w))
+        perm = torch.cat(order)
+        pred = torch.cat(trajs, dim=1).to(trajectories.dtype)[None]
+        return (trajectories[:, :, perm], visibilities[:, :, perm], pred, torch.zeros_like(visibilities),
+                query_points[:, perm])
+
+    # -------------------------------------------------- VOS-style entry (mask labels)
+    @torch.no_grad()
+    def propagate_masks(self, feats, ref_seg, out_hw, num_classes=None):
+        """feats [T,C,Hf,Wf]; ref_seg int [Hf,Wf] (first-frame mask already at feature
+        resolution).  Returns (label maps [T,L,Hf,Wf], uint8 masks [T,h,w]) with the
+        decode of vanilla_tracker.py:769-798."""
+        cfg = self.test_cfg
+        T, C, Hf, Wf = feats.shape
+        dev = feats.device
+        onehot = torch.nn.functional.one_hot(ref_seg.long().to(dev), num_classes).permute(2, 0, 1).float().contiguous()
+        L = onehot.shape[0]
+        bank = FeatureBank(T, C, Hf, Wf, dev)
+        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
+        table = JobTable()
+        nr = cfg.get("neighbor_range", None)
+        unmasked_first = 0 if cfg.get("with_first_neighbor", True) else 1
+        for t in range(1, T):
+            mem = engine.memory_frames(t, cfg.precede_frames, cfg.get("with_first", True))
+            table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
+        labels = LabelBank(T, L, Hf, Wf, dev)
+        labels.put_nchw(onehot, 0)
+        maps = torch.empty(T, L, Hf, Wf, dtype=torch.float32, device=dev)
+        masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=dev)
+        maps[0] = onehot
+        masks[0] = engine.decode_masks(maps[0], out_hw)
+        if T > 1:
+            lists = engine.affinity_topk(bank, table, (nr // 2) if nr is not None else 1, cfg.topk,
+                                         cfg.get("mask_mode", "circle"), engine=self.engine_id)
+        for t in range(1, T):
+            engine.gather_labels(lists, table, t - 1, t, labels, cfg.temperature)
+            labels.get_nchw(t, out=maps[t])
+            masks[t] = engine.decode_masks(maps[t], out_hw)
+        return maps, masks
+
+
+B200VanillaTracker = VanillaTracker
+
+
+def register_in_mmpt():
+    """Inside an mmpt installation: make ``eval_arc='B200VanillaTracker'`` resolvable."""
+    from mmpt.models.registry import MODELS
+    MODELS.register_module(name="B200VanillaTracker", module=VanillaTracker)
+    return MODELS

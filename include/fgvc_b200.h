@@ -1,0 +1,161 @@
+/*
+ * fgvc_b200 -- C ABI of the B200-native label-propagation path of FGVC (mmpt).
+ *
+ * This is the drop-in boundary: plain C, device pointers + sizes, no torch types.
+ * The Python host (fgvc_b200/ops.py, tracker.py) binds it with ctypes; a maintainer of
+ * the reference would bind exactly these symbols.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer; the library allocates nothing persistent except a
+ *     small cache of TMA descriptors;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, and returns 0 on success or a negative fgvc_status; the message is
+ *     available from fgvc_last_error() (thread local);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Data layout in HBM (all fp32 unless noted)
+ *   feature bank  feat[slot][2][H*W][C]   part 0 = TF32-rounded "hi", part 1 = x - hi
+ *                 ("lo"); rows are L2-normalised over C; pixel-major so that the channel
+ *                 (contraction) dimension is contiguous = K-major MMA operands.
+ *   label bank    lab[slot][H*W][Lp]      Lp = L rounded up to a multiple of 4 (float4
+ *                 rows); pixel-major so that the k winners of a query are k coalesced rows.
+ *   top-k lists   val[job][group][Nq][K], idx[job][group][Nq][K] (int32,
+ *                 idx = position_in_memory_list * Nk + key_pixel, -1 = empty), sorted
+ *                 descending; val is the raw cosine (not yet divided by the temperature).
+ *
+ * Reference interfaces replaced (paths relative to the FGVC repository):
+ *   mmpt/models/common/local_attention.py:267  masked_attention_efficient
+ *   mmpt/models/common/local_attention.py:392  masked_attention_efficient_v2
+ *   mmpt/models/common/local_attention.py:721  masked_attention_efficient_c2f
+ *   mmpt/models/common/affinity_utils.py:75    spatial_neighbor (folded into the kernels)
+ *   mmpt/models/trackers/vanilla_tracker.py:172 img2coord, :204 draw_gaussion_map_online,
+ *                                           :305 forward_test_main (per-frame loop)
+ */
+#ifndef FGVC_B200_H_
+#define FGVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGVC_VERSION 100
+
+#if defined(__GNUC__)
+#define FGVC_API __attribute__((visibility("default")))
+#else
+#define FGVC_API
+#endif
+
+typedef enum fgvc_status {
+  FGVC_OK = 0,
+  FGVC_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  FGVC_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  FGVC_ERR_UNSUPPORTED = -3  /* valid in the reference but not built here */
+} fgvc_status;
+
+typedef enum fgvc_mask_mode { FGVC_MASK_CIRCLE = 0, FGVC_MASK_SQUARE = 1 } fgvc_mask_mode;
+
+/* affinity engines of K1.  AUTO picks the tcgen05 kernel whenever the shape allows
+ * (C % 32 == 0, K <= 16); SIMT is the exact-fp32 CUDA-core kernel for every other shape. */
+typedef enum fgvc_engine { FGVC_ENGINE_AUTO = 0, FGVC_ENGINE_SIMT = 1, FGVC_ENGINE_TCGEN05 = 2 } fgvc_engine;
+
+/* One propagation job = one query frame and its memory list (a multiset of frames:
+ * frame 0 appears twice while t <= precede_frames, vanilla_tracker.py:346-362). */
+typedef struct fgvc_job {
+  int32_t q_slot;     /* feature-bank slot of the query frame */
+  int32_t mem_begin;  /* memory entries [mem_begin, mem_end) of the mem_* tables */
+  int32_t mem_end;
+  int32_t out_slot;   /* label-bank slot written by fgvc_gather_labels */
+} fgvc_job;
+
+#define FGVC_MEM_UNMASKED 0x40000000 /* OR into mem_feat_slot: radius mask not applied
+                                        (the first non_mask_len frames, local_attention.py:347) */
+
+FGVC_API const char* fgvc_last_error(void);
+FGVC_API int fgvc_version(void);
+/* number of CUDA devices visible to the library (0 => every compute call fails) */
+FGVC_API int fgvc_device_count(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+FGVC_API int64_t fgvc_launch_count(void);
+
+/* K0 -- F.normalize(dim=C) + NCHW -> pixel-major + TF32 hi/lo split
+ * (local_attention.py:308-310).  src: n_frames frames of [C][H*W], consecutive frames
+ * src_frame_stride floats apart, channels src_chan_stride floats apart (so a
+ * [1,C,T,H,W] key stack can be read in place).  Writes bank slots
+ * first_slot .. first_slot+n_frames-1. */
+FGVC_API int fgvc_prep_features(const float* src, int64_t src_frame_stride, int64_t src_chan_stride,
+                       int32_t n_frames, int32_t C, int32_t H, int32_t W, int32_t normalize,
+                       float* feat_bank, int32_t first_slot, void* stream);
+
+/* label layout conversions: NCHW [L][H*W] (channel stride src_chan_stride) <-> pixel-major */
+FGVC_API int fgvc_labels_to_pixmajor(const float* src, int64_t src_chan_stride, int32_t L, int32_t n_pix,
+                            float* lab_bank, int32_t slot, int32_t Lp, void* stream);
+FGVC_API int fgvc_labels_to_nchw(const float* lab_bank, int32_t slot, int32_t Lp, int32_t L, int32_t n_pix,
+                        float* dst, void* stream);
+
+/* draw_gaussion_map_online at feature resolution (vanilla_tracker.py:204-221):
+ * lab[slot][y*W+x][p] = exp(-((x*stride-px)^2 + (y*stride-py)^2) / (2 sigma^2)).
+ * points_xy: [P][2] (x,y) image pixels. */
+FGVC_API int fgvc_gaussian_labels(const float* points_xy, int32_t P, int32_t H, int32_t W, int32_t stride,
+                         float sigma, float* lab_bank, int32_t slot, int32_t Lp, void* stream);
+
+/* 1 when the tcgen05 engine of K1 takes this shape, else 0 (AUTO then uses the SIMT engine) */
+FGVC_API int fgvc_tc_supported(int32_t H, int32_t W, int32_t C, int32_t K);
+
+/* workspace bytes for the top-k lists of n_jobs jobs */
+FGVC_API int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K);
+
+/* K1 -- affinity + radius mask + running top-K for jobs[0..n_jobs) in ONE launch
+ * (local_attention.py:318-356 without materialising the affinity).  The memory list of
+ * each job is split into `groups` contiguous parts (load balance for short job lists);
+ * fgvc_gather_labels merges them.  K in [1,16]; radius = neighbor_range // 2. */
+FGVC_API int fgvc_affinity_topk(const float* feat_bank, int32_t H, int32_t W, int32_t C,
+                       const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
+                       float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
+
+/* K1b -- merge groups, /temperature, softmax over the K winners, gather + weighted sum
+ * of label rows (local_attention.py:360-374).  Handles jobs[job_begin..job_end) (the
+ * jobs of one time step across clips: they must not read each other's out_slot). */
+FGVC_API int fgvc_gather_labels(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
+                       const fgvc_job* jobs, int32_t job_begin, int32_t job_end,
+                       const int32_t* mem_label_slot, int32_t n_pix, float temperature,
+                       float* lab_bank, int32_t Lp, void* stream);
+
+/* K3 -- F.interpolate(bilinear, align_corners=False) to (out_h,out_w) fused with img2coord
+ * (vanilla_tracker.py:396-400, :172-191): top-5 soft-argmax, all-zero map -> -1.
+ * maps: n_maps channel-major maps [H*W]; out_xy: [n_maps][2]. */
+FGVC_API int fgvc_heatmap_coords(const float* maps, int32_t n_maps, int32_t H, int32_t W, int32_t out_h,
+                        int32_t out_w, int32_t topk, float* out_xy, void* stream);
+/* same on the analytic full-resolution gaussian of frame 0 (vanilla_tracker.py:321-343) */
+FGVC_API int fgvc_gaussian_coords(const float* points_xy, int32_t P, int32_t out_h, int32_t out_w,
+                         float sigma, int32_t topk, float* out_xy, void* stream);
+
+/* VOS-style decode (vanilla_tracker.py:769-798): bilinear up-sample, per-channel min-max
+ * normalise where max > 0, argmax over channels -> uint8 [out_h][out_w].
+ * maps: [L][H*W]; scratch_minmax: [2*L] floats. */
+FGVC_API int fgvc_decode_masks(const float* maps, int32_t L, int32_t H, int32_t W, int32_t out_h,
+                      int32_t out_w, float* scratch_minmax, uint8_t* out_mask, void* stream);
+
+/* K2 -- coarse-to-fine propagation (local_attention.py:721-880), single query frame.
+ * Coarse stage = per-memory-frame masked argmax on the coarse bank (K1 with K=1 per
+ * frame); fine stage = (2*radius_fine+1)^2 window of the fine bank centred at
+ * scale*(ky,kx), zero padded (padded candidates: affinity 0, value 0), top-K over
+ * T*R^2, softmax, gather of FINE labels.  Output on the coarse grid: out[Hc*Wc][Lp].
+ * job_dev / job_host: the same job in device memory (read by K1) and host memory (read by
+ * the launcher); scratch_val / scratch_idx: n_mem * Hc*Wc elements each. */
+FGVC_API int fgvc_c2f_propagate(const float* coarse_bank, int32_t Hc, int32_t Wc, int32_t C,
+                       const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
+                       const fgvc_job* job_dev, const fgvc_job* job_host,
+                       const int32_t* mem_feat_slot, const int32_t* mem_label_slot, int32_t radius,
+                       int32_t mask_mode, int32_t radius_fine, int32_t K, float temperature,
+                       const float* fine_lab_bank, int32_t Lp, float* out, float* scratch_val,
+                       int32_t* scratch_idx, int32_t engine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGVC_B200_H_ */

@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: job tables, memory multisets, sharding, the
+distributed collect (gloo, world_size 2) and the API surface / error behaviour."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from fgvc_b200 import apis, engine, ops
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_memory_frames_match_oracle():
+    for t in range(1, 12):
+        for p in (2, 5):
+            for wf in (True, False):
+                assert engine.memory_frames(t, p, wf) == O.memory_frames(t, p, wf)
+    # grouped clips start at t0: the window is clipped at t0 and t0 is "first"
+    assert engine.memory_frames(5, 2, True, first=3) == [3, 3, 4]
+    assert engine.memory_frames(4, 5, True, first=3) == [3, 3]
+
+
+def test_job_table_layout():
+    tb = engine.JobTable()
+    tb.add(1, [0, 0], [0, 0], 1)
+    tb.add(2, [0, 0, 1], [0, 0, 1], 2, unmasked=1)
+    assert tb.jobs == [(1, 0, 2, 1), (2, 2, 5, 2)]
+    assert tb.mem_feat[2] == (0 | 0x40000000) and tb.mem_feat[3] == 0
+    assert tb.max_mem == 3 and len(tb) == 2
+    j, mf, ml = tb.device("cpu")
+    assert j.dtype == torch.int32 and j.shape == (2, 4) and mf.shape == (5,)
+
+
+def test_pick_groups_fills_the_chip():
+    assert engine.pick_groups(1, 60, 107, 21) >= 2          # one DAVIS frame: split the memory
+    assert engine.pick_groups(63, 60, 107, 21) == 1         # a whole clip already fills 148 SMs
+    assert engine.pick_groups(1, 8, 8, 3) == 3              # never more groups than memory frames
+
+
+def test_sampler_matches_reference_sharding():
+    ds = list(range(10))
+    for world in (1, 2, 4):
+        for rank in range(world):
+            s = apis.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=False)
+            assert list(iter(s)) == O.shard_indices(10, rank, world)
+    with pytest.raises(ValueError):
+        apis.DistributedSampler(list(range(3)), num_replicas=4, rank=0, shuffle=False)
+
+
+def test_spatial_neighbor_matches_golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "masks.npz"))
+    for key in d.files:
+        mode, H, W, nr = key.split("_")
+        m = ops.spatial_neighbor(2, int(H), int(W), int(nr), "cpu", torch.float32, mode=mode)
+        m_ = m.as_subclass(torch.Tensor)
+        got = m_.numpy() if mode == "circle" else m_[0].numpy()
+        assert (got == d[key]).all(), key
+        assert ops._mask_spec(m, int(H), int(W), int(H), int(W)) == (mode, int(nr) // 2)
+
+
+def test_mask_radius_recovered_from_plain_tensor():
+    for mode, nr in (("circle", 8), ("square", 6), ("circle", 3)):
+        m = ops.spatial_neighbor(1, 11, 13, nr, "cpu", torch.float32, mode=mode).as_subclass(torch.Tensor).clone()
+        assert ops._mask_spec(m, 11, 13, 11, 13) == (mode, nr // 2)
+    bad = torch.rand(11 * 13, 11 * 13) > 0.5
+    with pytest.raises(NotImplementedError):
+        ops._mask_spec(bad, 11, 13, 11, 13)
+
+
+def test_unsupported_modes_raise_loudly():
+    q, k, v = torch.randn(1, 32, 4, 4), torch.randn(1, 32, 1, 4, 4), torch.rand(1, 2, 1, 4, 4)
+    with pytest.raises(NotImplementedError):
+        ops.masked_attention_efficient(q, k, v, None, topk=None)
+    with pytest.raises(NotImplementedError):
+        ops.masked_attention_efficient(q, k, v, None, topk=5, mode="cosine")
+    with pytest.raises(NotImplementedError):
+        ops.masked_attention_efficient(q, k, v, None, topk=5, sim_mode="l2-distance")
+    with pytest.raises(AssertionError):
+        ops.masked_attention_efficient(q, k, v, None, topk=5, mode="bogus")
+
+
+def test_encoder_contract():
+    from fgvc_b200.encoder import ResNetEncoder
+    torch.manual_seed(0)
+    enc = ResNetEncoder(depth=18, strides=(1, 2, 2, 1), out_indices=(2,), pool_type="none").eval()
+    with torch.no_grad():
+        y = enc(torch.randn(1, 3, 64, 96))
+    assert y.shape == (1, 256, 8, 12) and (y >= 0).all()
+    keys = enc.state_dict().keys()
+    for k in ("conv1.conv.weight", "conv1.bn.running_mean", "layer3.0.downsample.conv.weight",
+              "layer2.1.conv2.bn.weight"):
+        assert k in keys
+
+
+class _FakeModel(torch.nn.Module):
+    def forward(self, test_mode=True, save_image=False, save_path=None, iteration=None, vid=None):
+        i = int(vid[0])
+        return (torch.full((1, 3, 2, 2), float(i)), torch.arange(i + 1, dtype=torch.float64), f"video{i}")
+
+
+def _worker(rank, world, port, gpu_collect, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ds = [dict(vid=torch.tensor([i])) for i in range(5)]
+    sampler = apis.DistributedSampler(ds, shuffle=False)
+    loader = torch.utils.data.DataLoader(ds, batch_size=None, sampler=sampler)
+    res = apis.multi_gpu_test(_FakeModel(), loader, gpu_collect=gpu_collect)
+    if rank == 0:
+        q.put([(float(r[0].mean()), r[1].tolist(), r[2]) for r in res])
+    else:
+        assert res is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gpu_collect", [True, False])
+def test_multi_gpu_test_world2_gloo(gpu_collect):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29511 + int(gpu_collect)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, gpu_collect, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g[2] for g in got] == [f"video{i}" for i in range(5)]          # reference order, padding cut
+    assert [g[0] for g in got] == [float(i) for i in range(5)]
+    assert got[3][1] == [0.0, 1.0, 2.0, 3.0]

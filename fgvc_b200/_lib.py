@@ -40,12 +40,13 @@ SIGNATURES = {
     "fgvc_gaussian_labels": (I, [P, I, I, I, I, F, P, I, I, P]),
     "fgvc_tc_supported": (I, [I, I, I, I]),
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
-    "fgvc_affinity_topk": (I, [P, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
+    "fgvc_affinity_topk": (I, [P, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
+    "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
     "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, P, I, P]),
     "fgvc_heatmap_coords": (I, [P, I, I, I, I, I, I, P, P]),
     "fgvc_gaussian_coords": (I, [P, I, I, I, F, I, P, P]),
     "fgvc_decode_masks": (I, [P, I, I, I, I, I, P, P, P]),
-    "fgvc_c2f_propagate": (I, [P, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
+    "fgvc_c2f_propagate": (I, [P, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
 }
 
 _lib = None

@@ -135,7 +135,7 @@ static int launch_fine(const float* fine_bank, int Hc, int Wc, int Hf, int Wf, i
 
 using namespace fgvc;
 
-extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t Hc, int32_t Wc, int32_t C,
+extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t n_slots, int32_t Hc, int32_t Wc, int32_t C,
                                   const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
                                   const fgvc_job* job_dev, const fgvc_job* job_host, const int32_t* mem_feat_slot,
                                   const int32_t* mem_label_slot, int32_t radius, int32_t mask_mode,
@@ -151,7 +151,7 @@ extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t Hc, int32_t 
   const int n_mem = job_host->mem_end - job_host->mem_begin;
   FGVC_CHECK_ARG(n_mem >= 1 && n_mem <= 64, "fgvc_c2f_propagate: memory length %d not in [1,64]", n_mem);
   // coarse stage: top-1 per memory frame == groups = n_mem
-  int rc = fgvc_affinity_topk(coarse_bank, Hc, Wc, C, job_dev, 1, mem_feat_slot, radius, mask_mode, 1, n_mem,
+  int rc = fgvc_affinity_topk(coarse_bank, n_slots, Hc, Wc, C, job_dev, 1, mem_feat_slot, radius, mask_mode, 1, n_mem,
                               scratch_val, scratch_idx, engine, stream);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;

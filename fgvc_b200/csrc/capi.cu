@@ -53,12 +53,12 @@ static int pick_engine(int engine, int H, int W, int C, int K, bool* use_tc) {
   return FGVC_OK;
 }
 
-extern "C" int fgvc_affinity_topk(const float* feat_bank, int32_t H, int32_t W, int32_t C, const fgvc_job* jobs,
-                                  int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius, int32_t mask_mode,
-                                  int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx, int32_t engine,
-                                  void* stream) {
+static int affinity_topk_impl(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                              const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius,
+                              int32_t mask_mode, int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx,
+                              int32_t engine, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes, void* stream) {
   FGVC_CHECK_ARG(feat_bank && jobs && mem_feat_slot && topk_val && topk_idx, "fgvc_affinity_topk: null pointer");
-  FGVC_CHECK_ARG(H > 0 && W > 0 && C > 0 && n_jobs > 0, "fgvc_affinity_topk: bad shape");
+  FGVC_CHECK_ARG(H > 0 && W > 0 && C > 0 && n_jobs > 0 && n_slots > 0, "fgvc_affinity_topk: bad shape");
   FGVC_CHECK_ARG(K >= 1 && K <= 16, "fgvc_affinity_topk: topk=%d not in [1,16]", K);
   FGVC_CHECK_ARG(groups >= 1 && groups <= 64, "fgvc_affinity_topk: groups=%d not in [1,64]", groups);
   FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk: radius=%d must be >= 1", radius);
@@ -68,8 +68,26 @@ extern "C" int fgvc_affinity_topk(const float* feat_bank, int32_t H, int32_t W, 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc)
-    return launch_affinity_topk_tc(feat_bank, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
-                                   topk_val, topk_idx, st);
+    return launch_affinity_topk_tc(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                                   groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
   return launch_affinity_topk_simt(feat_bank, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
                                    topk_val, topk_idx, st);
+}
+
+extern "C" int fgvc_affinity_topk(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                                  const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius,
+                                  int32_t mask_mode, int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx,
+                                  int32_t engine, void* stream) {
+  return affinity_topk_impl(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
+                            topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int fgvc_debug_affinity_boxes(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                                         const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                                         int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,
+                                         int32_t* topk_idx, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes,
+                                         void* stream) {
+  FGVC_CHECK_ARG(dbg && dbg_meta && dbg_max_boxes > 0, "fgvc_debug_affinity_boxes: null debug buffers");
+  return affinity_topk_impl(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, 1,
+                            topk_val, topk_idx, FGVC_ENGINE_TCGEN05, dbg, dbg_meta, dbg_max_boxes, stream);
 }

@@ -61,6 +61,19 @@ struct TopK {
     }
   }
   __device__ __forceinline__ float thr() const { return v[K - 1]; }
+  // variant for exact ties: a later (higher-index) equal value goes ahead of earlier ones,
+  // like a stable ascending argsort read from the back (np.argsort in img2coord)
+  __device__ __forceinline__ void push_ge(float x, int i) {
+    v[K - 1] = x;
+    id[K - 1] = i;
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+      if (v[j] >= v[j - 1]) {
+        float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+        int ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+      }
+    }
+  }
   // caller guarantees x > thr()
   __device__ __forceinline__ void push(float x, int i) {
     v[K - 1] = x;
@@ -88,9 +101,10 @@ __host__ __device__ inline int mask_reach(int r, int mode) { return mode == FGVC
 int launch_affinity_topk_simt(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups,
                               float* tv, int32_t* ti, cudaStream_t st);
-int launch_affinity_topk_tc(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                             const int32_t* mem_feat, int radius, int mode, int K, int groups,
-                            float* tv, int32_t* ti, cudaStream_t st);
+                            float* tv, int32_t* ti, float* dbg, int32_t* dbg_meta, int dbg_max_boxes,
+                            cudaStream_t st);
 bool tc_supported(int H, int W, int C, int K);
 
 }  // namespace fgvc

@@ -62,7 +62,7 @@ __device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk
     int oy = o / out_w, ox = o - oy * out_w;
     float v = src.at(oy, ox);
     sum += (double)v;
-    if (v > top.thr()) top.push(v, o);
+    if (v >= top.thr()) top.push_ge(v, o);   // ties: the higher index wins
   }
   // all-zero test: np.sum(map) == 0
 #pragma unroll
@@ -72,17 +72,17 @@ __device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk
   int head = 0;
   for (int r = 0; r < topk; ++r) {
     float v = -INFINITY;
-    int i = 0x7fffffff;
+    int i = -1;
 #pragma unroll
     for (int j = 0; j < CK; ++j)
-      if (j == head) { v = top.v[j]; i = top.id[j] < 0 ? 0x7fffffff : top.id[j]; }
+      if (j == head) { v = top.v[j]; i = top.id[j]; }
     int t = tid;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, v, o);
       int oi = __shfl_xor_sync(0xffffffffu, i, o);
       int ot = __shfl_xor_sync(0xffffffffu, t, o);
-      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; t = ot; }
+      if (ov > v || (ov == v && oi > i)) { v = ov; i = oi; t = ot; }
     }
     __syncthreads();
     if (lane == 0) { red_v[warp] = v; red_i[warp] = i; red_t[warp] = t; }
@@ -90,7 +90,7 @@ __device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk
     float bv = red_v[0]; int bi = red_i[0], bt = red_t[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w)
-      if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
+      if (red_v[w] > bv || (red_v[w] == bv && red_i[w] > bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
     if (tid == bt) ++head;
     if (tid == 0) { win_v[r] = bv; win_i[r] = bi; }
   }

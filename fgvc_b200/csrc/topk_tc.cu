@@ -1,10 +1,454 @@
-// K1 (tcgen05 engine) -- placeholder until the tensor-core kernel lands.
+// K1 (tcgen05 engine): fused affinity + radius mask + running top-K on the 5th-gen tensor
+// cores.  The (T*H*W) x (H*W) affinity of local_attention.py:321-356 never reaches HBM.
+//
+// One CTA = one 128-query tile (8x16 or 16x8 pixels, M = 128) of one job and one memory
+// group.  For every memory frame it walks the key boxes (BH rows x 16 columns, N = 16*BH)
+// covering the radius halo of the tile -- image-clipped, corner boxes outside every
+// query's mask skipped -- and for each box:
+//   warp 0      TMA producer: per 32-channel chunk, cp.async.bulk.tensor (5-D map over
+//               feat[slot][part][H][W][C], 128B swizzle) of the query tile (hi, lo) and the
+//               key box (hi, lo) into a 3-stage shared-memory ring; out-of-image pixels are
+//               zero-filled by the TMA unit, so halos need no branches.
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma kind::tf32, M=128 x N x K=8,
+//               three products per K step -- lo*hi + hi*lo + hi*hi (3xTF32: fp32-faithful
+//               selection) -- accumulating in one TMEM tile; two TMEM tiles ping-pong
+//               between the tensor pipe and the epilogue.
+//   warps 2..5  epilogue: thread = query (TMEM lane).  tcgen05.ld pulls 16 columns (one key
+//               row) at a time; the analytic circle / square mask and the image bounds are a
+//               16-bit interval mask per key row; survivors above the running K-th value are
+//               inserted into the thread's sorted top-K list held in registers.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers
+// (MMA <-> epilogue).  A 128 x N fp32 tile costs N*128*4 B of TMEM reads and no HBM.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace fgvc {
-bool tc_supported(int, int, int, int) { return false; }
-int launch_affinity_topk_tc(const float*, int, int, int, const fgvc_job*, int, const int32_t*, int, int, int, int,
-                            float*, int32_t*, cudaStream_t) {
-  set_error("tcgen05 engine not built");
-  return FGVC_ERR_UNSUPPORTED;
+
+constexpr int TC_STAGES = 3;
+constexpr int TC_STAGE_BYTES = 64 * 1024;        // A_hi 16K | A_lo 16K | B_hi <=16K | B_lo <=16K
+constexpr int TC_MAX_BH = 8;                     // N <= 128 (two accumulators = 256 TMEM columns)
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*barriers, tables*/ + 1024 /*align*/;
+
+struct TcParams {
+  int H, W, C, n_pix;
+  int radius, mode, reach;
+  int QH, QW, qw_shift;      // query tile (8x16 or 16x8)
+  int BH;                    // key box rows; N = 16 * BH
+  int groups, k_out;
+  int tiles_x;
+  const fgvc_job* jobs;
+  const int32_t* mem_feat;
+  float* tv;
+  int32_t* ti;
+  float* dbg;                // optional raw affinity dump [box][128][128]
+  int32_t* dbg_meta;         // [box][4] = (mem entry, by, bx, N)
+  int dbg_max_boxes;
+};
+
+// ------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, cta_group::1
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13), K-major both,
+// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- the box walk, evaluated identically by every warp role ---------------------------
+struct Walk {
+  int y_lo, y_hi, x_lo, x_hi;   // key rectangle (inclusive) for this memory entry
+  bool masked;
+};
+__device__ __forceinline__ Walk make_walk(const TcParams& p, int raw, int qy0, int qx0) {
+  Walk w;
+  w.masked = !(raw & FGVC_MEM_UNMASKED);
+  if (w.masked) {
+    w.y_lo = max(0, qy0 - p.reach); w.y_hi = min(p.H - 1, qy0 + p.QH - 1 + p.reach);
+    w.x_lo = max(0, qx0 - p.reach); w.x_hi = min(p.W - 1, qx0 + p.QW - 1 + p.reach);
+  } else {
+    w.y_lo = 0; w.y_hi = p.H - 1; w.x_lo = 0; w.x_hi = p.W - 1;
+  }
+  return w;
+}
+// true when no query of the tile can have an in-mask key inside the box
+__device__ __forceinline__ bool box_skipped(const TcParams& p, const Walk& w, int by, int bx, int qy0, int qx0) {
+  if (!w.masked) return false;
+  int qy1 = min(p.H - 1, qy0 + p.QH - 1), qx1 = min(p.W - 1, qx0 + p.QW - 1);
+  int by1 = min(p.H - 1, by + p.BH - 1), bx1 = min(p.W - 1, bx + 15);
+  int dy = max(0, max(by - qy1, qy0 - by1));
+  int dx = max(0, max(bx - qx1, qx0 - bx1));
+  return !in_mask(dy, dx, p.radius, p.mode);
+}
+
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_STAGES;    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);   // [reach+1] <= 128 entries
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qy0 = (blockIdx.x / p.tiles_x) * p.QH, qx0 = (blockIdx.x % p.tiles_x) * p.QW;
+  const int g = blockIdx.y;
+  const fgvc_job job = p.jobs[blockIdx.z];
+  const int n_mem = job.mem_end - job.mem_begin;
+  const int per = (n_mem + p.groups - 1) / p.groups;
+  const int e_lo = job.mem_begin + g * per;
+  const int e_hi = min(job.mem_end, e_lo + per);
+  const int N = 16 * p.BH;
+  const int n_kc = p.C / 32;
+  const uint32_t b_bytes = (uint32_t)N * 128u;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int d = threadIdx.x; d <= p.reach; d += TC_THREADS) {
+    int hw = -1;
+    if (p.mode == FGVC_MASK_CIRCLE) {
+      while (hw + 1 <= p.reach && (hw + 1) * (hw + 1) + d * d < p.radius * p.radius) ++hw;
+    } else {
+      hw = p.radius;
+    }
+    halfw[d] = hw;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int e = e_lo; e < e_hi; ++e) {
+        const int raw = p.mem_feat[e];
+        const int slot = raw & ~FGVC_MEM_UNMASKED;
+        const Walk w = make_walk(p, raw, qy0, qx0);
+        for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
+          for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
+            if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+            for (int kc = 0; kc < n_kc; ++kc) {
+              mbar_wait(empty_bar + stage, phase ^ 1);
+              uint8_t* st = smem + stage * TC_STAGE_BYTES;
+              mbar_expect_tx(full_bar + stage, 2u * 16384u + 2u * b_bytes);
+              tma_load_5d(&tmap_q, full_bar + stage, st, kc * 32, qx0, qy0, 0, job.q_slot);
+              tma_load_5d(&tmap_q, full_bar + stage, st + 16384, kc * 32, qx0, qy0, 1, job.q_slot);
+              tma_load_5d(&tmap_k, full_bar + stage, st + 32768, kc * 32, bx, by, 0, slot);
+              tma_load_5d(&tmap_k, full_bar + stage, st + 49152, kc * 32, bx, by, 1, slot);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================= MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, N);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, tphase[2] = {0, 0};
+      for (int e = e_lo; e < e_hi; ++e) {
+        const int raw = p.mem_feat[e];
+        const Walk w = make_walk(p, raw, qy0, qx0);
+        for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
+          for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
+            if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+            mbar_wait(tempty_bar + buf, tphase[buf] ^ 1);     // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+            for (int kc = 0; kc < n_kc; ++kc) {
+              mbar_wait(full_bar + stage, phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+              const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + 16384);
+              const uint64_t b_hi = make_desc(sa + 32768), b_lo = make_desc(sa + 49152);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 8 tf32 = 32 B) per 128 B swizzle row
+                const uint64_t o = (uint64_t)(ks * 2);  // +32 B in the >>4 start-address field
+                umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kc | ks) != 0);
+                umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
+                umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+              }
+              umma_commit(empty_bar + stage);         // smem slot free once these MMAs retire
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar + buf);             // accumulator complete
+            tphase[buf] ^= 1;
+            buf ^= 1;
+          }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================== epilogue ======================================
+    const int lg = warp & 3;                          // TMEM lane group this warp may access
+    const int m = lg * 32 + lane;                     // query row in the tile
+    const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
+    const bool qvalid = qy < p.H && qx < p.W;
+    TopK<K> top;
+    top.init();
+    int buf = 0;
+    uint32_t tphase[2] = {0, 0};
+    int box_seq = 0;
+    for (int e = e_lo; e < e_hi; ++e) {
+      const int raw = p.mem_feat[e];
+      const Walk w = make_walk(p, raw, qy0, qx0);
+      const int pos_base = (e - job.mem_begin) * p.n_pix;
+      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
+        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
+          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+          mbar_wait(tfull_bar + buf, tphase[buf]);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128);
+          for (int row = 0; row < p.BH; ++row) {
+            const int ky = by + row;
+            // 16-bit interval mask of the in-mask, in-image keys of this row
+            uint32_t bits = 0;
+            if (qvalid && ky < p.H) {
+              int lo, hi;
+              if (w.masked) {
+                int ady = abs(ky - qy);
+                int hw = ady <= p.reach ? halfw[ady] : -1;
+                lo = hw < 0 ? 1 : max(qx - hw, 0);
+                hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
+              } else {
+                lo = 0; hi = p.W - 1;
+              }
+              lo = max(lo - bx, 0);
+              hi = min(hi - bx, 15);
+              if (hi >= lo) bits = (2u << hi) - (1u << lo);
+            }
+            const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes;
+            if (!__any_sync(0xffffffffu, bits != 0) && !dump) continue;    // warp-uniform
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(row * 16), v);
+            if (dump) {
+              float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) d[j] = v[j];
+            }
+            if (bits) {
+              const int kbase = pos_base + ky * p.W + bx;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (((bits >> j) & 1u) && v[j] > top.thr()) top.push(v[j], kbase + j);
+            }
+          }
+          if (p.dbg_meta != nullptr && box_seq < p.dbg_max_boxes && m == 0) {
+            p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
+            p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
+          }
+          ++box_seq;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + buf);
+          tphase[buf] ^= 1;
+          buf ^= 1;
+        }
+    }
+    if (qvalid) {
+      const int q = qy * p.W + qx;
+      const int64_t o = (((int64_t)blockIdx.z * p.groups + g) * p.n_pix + q) * p.k_out;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (i < p.k_out) { p.tv[o + i] = top.v[i]; p.ti[o + i] = top.id[i]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// 5-D map over feat[slot][part][H][W][C]; box = (32 channels, bw, bh, 1, 1), 128B swizzle
+static int make_map(CUtensorMap* map, const float* bank, int n_slots, int H, int W, int C, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return FGVC_ERR_CUDA;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, 2, (cuuint64_t)n_slots};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4,
+                           (cuuint64_t)2 * H * W * C * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)bank, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (H=%d W=%d C=%d box=%dx%d)", (int)r, H, W, C, bw, bh);
+    return FGVC_ERR_CUDA;
+  }
+  return FGVC_OK;
+}
+
+bool tc_supported(int H, int W, int C, int K) {
+  return C % 32 == 0 && C >= 32 && C <= 1024 && K >= 1 && K <= 16 && H >= 1 && W >= 1;
+}
+
+// key-box rows (<= 8) for a halo of `rows` rows.  Per box and 32-channel chunk the CTA streams
+// 128 query rows + N key rows and issues MMAs for N columns, so cost ~ n_boxes * (128 + N).
+static int box_cost(int rows, int bh) { return cdiv(rows, bh) * (128 + 16 * bh); }
+static int pick_bh(int rows) {
+  int best = TC_MAX_BH;
+  for (int bh = TC_MAX_BH - 1; bh >= 1; --bh)
+    if (box_cost(rows, bh) < box_cost(rows, best)) best = bh;
+  return best;
+}
+
+template <int K>
+static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const TcParams& p, dim3 grid, cudaStream_t st) {
+  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TC_SMEM_BYTES));
+  affinity_topk_tc_kernel<K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mk, p);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+                            const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
+                            float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st) {
+  TcParams p;
+  p.H = H; p.W = W; p.C = C; p.n_pix = H * W;
+  p.radius = radius; p.mode = mode; p.reach = mask_reach(radius, mode);
+  // orientation of the 128-query tile: the one whose padded halo is smaller
+  const int reach = p.reach;
+  auto halo_cost = [&](int qh, int qw) {
+    int rows = min(H, qh + 2 * reach), cols = min(W, qw + 2 * reach);
+    double tiles = (double)cdiv(H, qh) * cdiv(W, qw);
+    return tiles * box_cost(rows, pick_bh(rows)) * cdiv(cols, 16);
+  };
+  if (halo_cost(16, 8) < halo_cost(8, 16)) { p.QH = 16; p.QW = 8; p.qw_shift = 3; }
+  else { p.QH = 8; p.QW = 16; p.qw_shift = 4; }
+  p.BH = pick_bh(min(H, p.QH + 2 * reach));
+  p.groups = groups; p.k_out = K;
+  p.tiles_x = cdiv(W, p.QW);
+  p.jobs = jobs; p.mem_feat = mem_feat; p.tv = tv; p.ti = ti;
+  p.dbg = dbg; p.dbg_meta = dbg_meta; p.dbg_max_boxes = dbg_max_boxes;
+  FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 engine: radius %d too large", radius);
+  CUtensorMap mq, mk;
+  int rc = make_map(&mq, bank, n_slots, H, W, C, p.QW, p.QH);
+  if (rc) return rc;
+  rc = make_map(&mk, bank, n_slots, H, W, C, 16, p.BH);
+  if (rc) return rc;
+  dim3 grid(cdiv(H, p.QH) * p.tiles_x, groups, n_jobs);
+  if (K <= 4) return launch_tc<4>(mq, mk, p, grid, st);
+  if (K <= 10) return launch_tc<10>(mq, mk, p, grid, st);
+  return launch_tc<16>(mq, mk, p, grid, st);
+}
+
 }  // namespace fgvc

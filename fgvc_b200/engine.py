@@ -136,7 +136,7 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
         lists = TopKLists(len(table), groups, bank.H * bank.W, K, dev)
     assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
-    call("fgvc_affinity_topk", ptr(bank.buf), bank.H, bank.W, bank.C, ptr(jobs), len(table), ptr(mem_feat),
+    call("fgvc_affinity_topk", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C, ptr(jobs), len(table), ptr(mem_feat),
          int(radius), mode, int(K), int(groups), ptr(lists.val), ptr(lists.idx), int(engine), stream_ptr())
     return lists
 
@@ -197,8 +197,62 @@ def c2f_propagate(coarse, fine, table, job_index, fine_labels, radius, radius_fi
     si = torch.empty(n_mem * nq, dtype=torch.int32, device=dev)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     jptr = ctypes.c_void_p(jobs.data_ptr() + 16 * job_index)
-    call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
+    call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.n_slots, coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
          jptr, ctypes.byref(hj), ptr(mem_feat), ptr(mem_label), int(radius), mode, int(radius_fine), int(K),
          float(temperature), ptr(fine_labels.buf), fine_labels.Lp, ptr(out), ptr(sv), ptr(si), int(engine),
          stream_ptr())
     return out
+
+
+class MaskClipPropagator:
+    """VOS-style propagation of one clip with pre-allocated banks (the loop of
+    vanilla_tracker.py:345-412 / :730-798 for mask labels): K0 over all frames, ONE K1 launch
+    over all frames' jobs, then per frame K1b gather -> NCHW -> decode (bilinear up-sample,
+    min-max normalise, argmax).  ``events=True`` records CUDA events around K1."""
+
+    def __init__(self, T, C, H, W, L, out_hw, cfg, device, engine_id=_lib.ENGINE_AUTO):
+        self.T, self.C, self.H, self.W, self.L, self.out_hw, self.cfg = T, C, H, W, L, tuple(out_hw), cfg
+        self.engine_id = engine_id
+        self.device = device
+        self.bank = FeatureBank(T, C, H, W, device)
+        self.labels = LabelBank(T, L, H, W, device)
+        self.table = JobTable()
+        nr = cfg.get("neighbor_range", None)
+        unmasked_first = 0 if cfg.get("with_first_neighbor", True) else 1
+        for t in range(1, T):
+            mem = memory_frames(t, cfg["precede_frames"], cfg.get("with_first", True))
+            self.table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
+        self.radius = (nr // 2) if nr is not None else 1
+        self.groups = pick_groups(len(self.table), H, W, self.table.max_mem) if T > 1 else 1
+        self.lists = TopKLists(max(1, len(self.table)), self.groups, H * W, cfg["topk"], device) if T > 1 else None
+        self.table.device(device)
+        self.maps = torch.empty(T, L, H, W, dtype=torch.float32, device=device)
+        self.masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(2 * L, dtype=torch.float32, device=device)
+        self.k1_events = None
+
+    def _decode(self, t):
+        call("fgvc_decode_masks", ptr(self.maps[t]), self.L, self.H, self.W, self.out_hw[0], self.out_hw[1],
+             ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
+
+    def run(self, feats, onehot0, events=False):
+        """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks)."""
+        cfg = self.cfg
+        self.bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
+        self.labels.put_nchw(onehot0, 0)
+        self.maps[0].copy_(onehot0)
+        self._decode(0)
+        if self.T > 1:
+            if events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            affinity_topk(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
+                          groups=self.groups, engine=self.engine_id, lists=self.lists)
+            if events:
+                e1.record()
+                self.k1_events = (e0, e1)
+        for t in range(1, self.T):
+            gather_labels(self.lists, self.table, t - 1, t, self.labels, cfg["temperature"])
+            self.labels.get_nchw(t, out=self.maps[t])
+            self._decode(t)
+        return self.maps, self.masks

@@ -159,33 +159,11 @@ class VanillaTracker(nn.Module):
         """feats [T,C,Hf,Wf]; ref_seg int [Hf,Wf] (first-frame mask already at feature
         resolution).  Returns (label maps [T,L,Hf,Wf], uint8 masks [T,h,w]) with the
         decode of vanilla_tracker.py:769-798."""
-        cfg = self.test_cfg
         T, C, Hf, Wf = feats.shape
         dev = feats.device
         onehot = torch.nn.functional.one_hot(ref_seg.long().to(dev), num_classes).permute(2, 0, 1).float().contiguous()
-        L = onehot.shape[0]
-        bank = FeatureBank(T, C, Hf, Wf, dev)
-        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
-        table = JobTable()
-        nr = cfg.get("neighbor_range", None)
-        unmasked_first = 0 if cfg.get("with_first_neighbor", True) else 1
-        for t in range(1, T):
-            mem = engine.memory_frames(t, cfg.precede_frames, cfg.get("with_first", True))
-            table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
-        labels = LabelBank(T, L, Hf, Wf, dev)
-        labels.put_nchw(onehot, 0)
-        maps = torch.empty(T, L, Hf, Wf, dtype=torch.float32, device=dev)
-        masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=dev)
-        maps[0] = onehot
-        masks[0] = engine.decode_masks(maps[0], out_hw)
-        if T > 1:
-            lists = engine.affinity_topk(bank, table, (nr // 2) if nr is not None else 1, cfg.topk,
-                                         cfg.get("mask_mode", "circle"), engine=self.engine_id)
-        for t in range(1, T):
-            engine.gather_labels(lists, table, t - 1, t, labels, cfg.temperature)
-            labels.get_nchw(t, out=maps[t])
-            masks[t] = engine.decode_masks(maps[t], out_hw)
-        return maps, masks
+        clip = engine.MaskClipPropagator(T, C, Hf, Wf, onehot.shape[0], out_hw, self.test_cfg, dev, self.engine_id)
+        return clip.run(feats.float().contiguous(), onehot)
 
 
 B200VanillaTracker = VanillaTracker

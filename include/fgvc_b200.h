@@ -112,10 +112,19 @@ FGVC_API int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query
  * (local_attention.py:318-356 without materialising the affinity).  The memory list of
  * each job is split into `groups` contiguous parts (load balance for short job lists);
  * fgvc_gather_labels merges them.  K in [1,16]; radius = neighbor_range // 2. */
-FGVC_API int fgvc_affinity_topk(const float* feat_bank, int32_t H, int32_t W, int32_t C,
+FGVC_API int fgvc_affinity_topk(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                        const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
+
+/* test hook (tcgen05 engine, groups = 1, use with ONE query tile): additionally dumps the
+ * raw 128 x 128 accumulator tile of the first dbg_max_boxes key boxes to
+ * dbg[box][query_row][key_col] and (mem entry, box y, box x, N) to dbg_meta[box][4]. */
+FGVC_API int fgvc_debug_affinity_boxes(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                       const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                       int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,
+                       int32_t* topk_idx, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes,
+                       void* stream);
 
 /* K1b -- merge groups, /temperature, softmax over the K winners, gather + weighted sum
  * of label rows (local_attention.py:360-374).  Handles jobs[job_begin..job_end) (the
@@ -147,7 +156,7 @@ FGVC_API int fgvc_decode_masks(const float* maps, int32_t L, int32_t H, int32_t 
  * T*R^2, softmax, gather of FINE labels.  Output on the coarse grid: out[Hc*Wc][Lp].
  * job_dev / job_host: the same job in device memory (read by K1) and host memory (read by
  * the launcher); scratch_val / scratch_idx: n_mem * Hc*Wc elements each. */
-FGVC_API int fgvc_c2f_propagate(const float* coarse_bank, int32_t Hc, int32_t Wc, int32_t C,
+FGVC_API int fgvc_c2f_propagate(const float* coarse_bank, int32_t n_slots, int32_t Hc, int32_t Wc, int32_t C,
                        const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
                        const fgvc_job* job_dev, const fgvc_job* job_host,
                        const int32_t* mem_feat_slot, const int32_t* mem_label_slot, int32_t radius,

@@ -255,7 +255,7 @@ def test_heatmap_coords_match_img2coord(golden_dir):
 
 def test_gaussian_labels_and_coords():
     from fgvc_b200 import engine
-    pts = torch.tensor([[10.3, 20.7], [50.0, 3.0], [0.0, 0.0], [79.0, 63.0]])
+    pts = torch.tensor([[10.3, 20.6], [50.1, 3.4], [0.2, 0.45], [78.9, 62.7]])   # no exactly equidistant pixels
     h, w, stride = 64, 80, 4
     full, small = O.gaussian_labels(pts, h, w, stride)
     bank = engine.LabelBank(2, 4, h // stride, w // stride, "cuda")

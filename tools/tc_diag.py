@@ -1,0 +1,103 @@
+"""GPU diagnostic for the tcgen05 engine (not a test): dumps the raw accumulator tiles of
+the first key boxes and compares them with <q,k> computed from the same feature bank.
+
+usage: python tools/tc_diag.py CASE     (run each case in its own process under `timeout`)
+"""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from fgvc_b200 import _lib, engine  # noqa: E402
+from fgvc_b200._lib import call, ptr, stream_ptr  # noqa: E402
+
+CASES = {
+    # name: (H, W, C, T, radius, topk)
+    "one_box_c32": (8, 16, 32, 1, 40, 10),
+    "one_box_c64": (8, 16, 64, 1, 40, 10),
+    "one_box_c256": (8, 16, 256, 1, 40, 10),
+    "halo_c64": (24, 48, 64, 2, 5, 10),
+    "ragged_c96": (13, 19, 96, 2, 4, 10),
+    "cfg1": (60, 107, 256, 6, 12, 10),
+}
+
+
+def main(name):
+    H, W, C, T, radius, K = CASES[name]
+    torch.manual_seed(0)
+    dev = "cuda"
+    feats = torch.randn(T + 1, C, H, W, device=dev)
+    bank = engine.FeatureBank(T + 1, C, H, W, dev)
+    bank.load_frames(feats)
+    table = engine.JobTable()
+    table.add(T, list(range(T)), list(range(T)), T)
+    jobs, mem_feat, _ = table.device(dev)
+    nq = H * W
+    maxb = 64
+    tv = torch.full((1, 1, nq, K), float("nan"), device=dev)
+    ti = torch.full((1, 1, nq, K), -7, dtype=torch.int32, device=dev)
+    dbg = torch.full((maxb, 128, 128), float("nan"), device=dev)
+    meta = torch.full((maxb, 4), -1, dtype=torch.int32, device=dev)
+    call("fgvc_debug_affinity_boxes", ptr(bank.buf), bank.n_slots, H, W, C, ptr(jobs), 1, ptr(mem_feat), radius, 0, K,
+         ptr(tv), ptr(ti), ptr(dbg), ptr(meta), maxb, stream_ptr())
+    torch.cuda.synchronize()
+    x = (bank.buf[:, 0] + bank.buf[:, 1]).double()          # [slot, pix, C]
+    meta = meta.cpu()
+    # NOTE: with several query tiles every CTA dumps into the same buffer; the LAST writer
+    # wins per box index, so only single-tile cases are exact here.  Use tile (0,0)'s view:
+    reach = radius - 1
+    qh, qw = (8, 16)
+    print(f"case {name}: H={H} W={W} C={C} T={T} r={radius}")
+    nb = int((meta[:, 0] >= 0).sum())
+    print("boxes dumped:", nb, meta[:min(nb, 6)].tolist())
+    if H <= 8 and W <= 16:
+        q = x[T].view(H, W, C)
+        worst = 0.0
+        for b in range(nb):
+            e, by, bx, N = meta[b].tolist()
+            k = x[e].view(H, W, C)
+            exp = torch.full((128, 128), float("nan"), dtype=torch.float64, device=dev)
+            for m in range(128):
+                qy, qx = m // qw, m % qw
+                if qy >= H or qx >= W:
+                    continue
+                for n in range(N):
+                    ky, kx = by + n // 16, bx + n % 16
+                    if 0 <= ky < H and 0 <= kx < W:
+                        exp[m, n] = (q[qy, qx] * k[ky, kx]).sum()
+            got = dbg[b].double()
+            ok = ~exp.isnan()
+            err = (got - exp)[ok].abs().max().item()
+            worst = max(worst, err)
+            print(f"  box {b} (e={e} by={by} bx={bx} N={N}): max |got-exp| = {err:.3e}; got[0,:4]={got[0,:4].tolist()} exp[0,:4]={exp[0,:4].tolist()}")
+            if err > 1e-4:
+                # help locating layout bugs: best matching expected column for a few got columns
+                g0 = got[:, :N][ok[:, :N].all(dim=1)]
+                e0 = exp[:, :N][ok[:, :N].all(dim=1)]
+                if g0.numel():
+                    for n in (0, 1, 2, 8, 16, 17):
+                        if n < N:
+                            d = (e0 - g0[:, n:n + 1]).abs().sum(0)
+                            print(f"    got col {n} best matches exp col {int(d.argmin())} (dist {float(d.min()):.2e})")
+                    gT = got[:N, :].t()
+        print("worst:", worst)
+    # end-to-end check of the lists against a dense fp64 computation
+    from oracle import oracle as O
+    kk = feats[:T].permute(1, 0, 2, 3)[None].cpu()
+    ex = O.propagate_exact(feats[T][None].cpu(), kk, torch.zeros(1, 1, T, H, W), radius=radius, topk=K)
+    got_idx = ti[0, 0].cpu().long()
+    want_idx = ex["idx"]
+    same = (got_idx.sort(1)[0] == want_idx.sort(1)[0]).all(1)
+    print("top-k sets equal for", int(same.sum()), "of", nq, "queries")
+    aff = (ex["aff"] - tv[0, 0].cpu().double()).abs()
+    aff = aff[~aff.isnan() & ~aff.isinf()]
+    print("max |affinity - exact| over winners:", float(aff.max()) if aff.numel() else None)
+    if not same.all():
+        bad = (~same).nonzero().flatten()[:5].tolist()
+        for qq in bad:
+            print("  q", qq, "got", got_idx[qq].tolist(), "want", want_idx[qq].tolist(), "tv", tv[0, 0, qq].tolist())
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -141,7 +141,7 @@ def run_ours(args):
     gathered = torch.empty((world,) + tuple(clip.masks.shape), dtype=torch.uint8, device=dev) if world > 1 else None
 
     def step(ev=False):
-        clip.run(feats, onehot, events=ev)
+        clip.run(feats, onehot, events=ev, want_maps=False)
         if world > 1:
             dist.all_gather_into_tensor(gathered, clip.masks)
 
@@ -191,7 +191,7 @@ def run_ours(args):
     def e2e_step():
         feats_dev.copy_(feats_host, non_blocking=True)
         onehot_dev.copy_(onehot_host, non_blocking=True)
-        clip.run(feats_dev, onehot_dev)
+        clip.run(feats_dev, onehot_dev, want_maps=False)
         masks_host.copy_(clip.masks, non_blocking=True)
 
     for _ in range(2):

@@ -106,5 +106,7 @@ int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C,
                             float* tv, int32_t* ti, float* dbg, int32_t* dbg_meta, int dbg_max_boxes,
                             cudaStream_t st);
 bool tc_supported(int H, int W, int C, int K);
+int launch_decode(const float* src, bool pixmajor, int L, int Lp, int H, int W, int out_h, int out_w,
+                  uint32_t* minmax, uint8_t* out, cudaStream_t st);
 
 }  // namespace fgvc

@@ -138,47 +138,105 @@ gaussian_coords_kernel(const float* __restrict__ pts, int out_h, int out_w, floa
 }
 
 // ---- VOS decode ----------------------------------------------------------------------
+// Label maps are read either channel-major (NCHW: maps[l][pix]) or straight from the
+// pixel-major label bank (lab[pix][Lp]).  Two passes over the OUTPUT pixels, one thread per
+// pixel: (1) per-channel min/max of the up-sampled map (warp shuffle -> shared -> one global
+// atomic per channel and block, on order-preserving uint keys), (2) normalise + argmax.
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct Tap {   // bilinear taps of one output pixel
+  int p00, p01, p10, p11;
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Tap make_tap(int oy, int ox, int H, int W, float sy, float sx) {
+  Lerp ly = lerp_coord(oy, sy, H), lx = lerp_coord(ox, sx, W);
+  Tap t;
+  t.p00 = ly.i0 * W + lx.i0; t.p01 = ly.i0 * W + lx.i1; t.p10 = ly.i1 * W + lx.i0; t.p11 = ly.i1 * W + lx.i1;
+  float w0x = 1.f - lx.w1, w0y = 1.f - ly.w1;
+  t.w00 = w0x; t.w01 = lx.w1; t.w10 = w0y; t.w11 = ly.w1;   // (x weights, y weights) kept separate
+  return t;
+}
+// same association as BilinearSrc::at: wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d)
+__device__ __forceinline__ float tap_val(const Tap& t, float a, float b, float c, float d) {
+  return t.w10 * (t.w00 * a + t.w01 * b) + t.w11 * (t.w00 * c + t.w01 * d);
+}
+
+template <bool PM>
+__device__ __forceinline__ float label_at(const float* __restrict__ src, int l, int pix, int stride_l, int stride_p) {
+  return __ldg(src + (int64_t)l * stride_l + (int64_t)pix * stride_p);
+}
+
+template <bool PM>
 __global__ void __launch_bounds__(256)
-decode_minmax_kernel(const float* __restrict__ maps, int H, int W, int out_h, int out_w,
-                     float* __restrict__ minmax) {
-  __shared__ float smn[8], smx[8];
-  const float* m = maps + (int64_t)blockIdx.x * H * W;
-  BilinearSrc src{m, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
-  float mn = INFINITY, mx = -INFINITY;
-  for (int o = threadIdx.x; o < out_h * out_w; o += 256) {
-    int oy = o / out_w, ox = o - oy * out_w;
-    float v = src.at(oy, ox);
-    mn = fminf(mn, v); mx = fmaxf(mx, v);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+decode_minmax_kernel(const float* __restrict__ src, int L, int H, int W, int stride_l, int stride_p, int out_h,
+                     int out_w, uint32_t* __restrict__ minmax /*[L] min keys, [L] max keys*/) {
+  extern __shared__ uint32_t skey[];   // [2L]
+  for (int i = threadIdx.x; i < 2 * L; i += 256) skey[i] = i < L ? 0xffffffffu : 0u;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-    minmax[2 * blockIdx.x] = mn; minmax[2 * blockIdx.x + 1] = mx;
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = o < out_h * out_w;
+  const int oy = valid ? o / out_w : 0, ox = valid ? o - oy * out_w : 0;
+  const Tap t = make_tap(oy, ox, H, W, (float)H / (float)out_h, (float)W / (float)out_w);
+  for (int l = 0; l < L; ++l) {
+    float v = tap_val(t, label_at<PM>(src, l, t.p00, stride_l, stride_p), label_at<PM>(src, l, t.p01, stride_l, stride_p),
+                      label_at<PM>(src, l, t.p10, stride_l, stride_p), label_at<PM>(src, l, t.p11, stride_l, stride_p));
+    float mn = valid ? v : INFINITY, mx = valid ? v : -INFINITY;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&skey[l], f2key(mn));
+      atomicMax(&skey[L + l], f2key(mx));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * L; i += 256) {
+    if (i < L) atomicMin(minmax + i, skey[i]);
+    else atomicMax(minmax + i, skey[i]);
   }
 }
 
+template <bool PM>
 __global__ void __launch_bounds__(256)
-decode_argmax_kernel(const float* __restrict__ maps, int L, int H, int W, int out_h, int out_w,
-                     const float* __restrict__ minmax, uint8_t* __restrict__ out) {
+decode_argmax_kernel(const float* __restrict__ src, int L, int H, int W, int stride_l, int stride_p, int out_h,
+                     int out_w, const uint32_t* __restrict__ minmax, uint8_t* __restrict__ out) {
   int o = blockIdx.x * 256 + threadIdx.x;
   if (o >= out_h * out_w) return;
   int oy = o / out_w, ox = o - oy * out_w;
+  const Tap t = make_tap(oy, ox, H, W, (float)H / (float)out_h, (float)W / (float)out_w);
   float best = -INFINITY;
   int arg = 0;
   for (int l = 0; l < L; ++l) {
-    BilinearSrc src{maps + (int64_t)l * H * W, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
-    float v = src.at(oy, ox);
-    float mn = __ldg(minmax + 2 * l), mx = __ldg(minmax + 2 * l + 1);
+    float v = tap_val(t, label_at<PM>(src, l, t.p00, stride_l, stride_p), label_at<PM>(src, l, t.p01, stride_l, stride_p),
+                      label_at<PM>(src, l, t.p10, stride_l, stride_p), label_at<PM>(src, l, t.p11, stride_l, stride_p));
+    float mn = key2f(__ldg(minmax + l)), mx = key2f(__ldg(minmax + L + l));
     if (mx > 0.f) v = __fdiv_rn(v - mn, (mx - mn) + 1e-12f);
     if (v > best) { best = v; arg = l; }
   }
   out[o] = (uint8_t)arg;
+}
+
+int launch_decode(const float* src, bool pixmajor, int L, int Lp, int H, int W, int out_h, int out_w,
+                  uint32_t* minmax, uint8_t* out, cudaStream_t st) {
+  FGVC_CUDA(cudaMemsetAsync(minmax, 0xff, (size_t)L * 4, st));
+  FGVC_CUDA(cudaMemsetAsync(minmax + L, 0x00, (size_t)L * 4, st));
+  const int blocks = cdiv(out_h * out_w, 256);
+  const int sl = pixmajor ? 1 : H * W, sp = pixmajor ? Lp : 1;
+  if (pixmajor) decode_minmax_kernel<true><<<blocks, 256, 2 * L * 4, st>>>(src, L, H, W, sl, sp, out_h, out_w, minmax);
+  else decode_minmax_kernel<false><<<blocks, 256, 2 * L * 4, st>>>(src, L, H, W, sl, sp, out_h, out_w, minmax);
+  FGVC_LAUNCH_CHECK();
+  if (pixmajor) decode_argmax_kernel<true><<<blocks, 256, 0, st>>>(src, L, H, W, sl, sp, out_h, out_w, minmax, out);
+  else decode_argmax_kernel<false><<<blocks, 256, 0, st>>>(src, L, H, W, sl, sp, out_h, out_w, minmax, out);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
 }
 
 }  // namespace fgvc
@@ -218,11 +276,15 @@ extern "C" int fgvc_decode_masks(const float* maps, int32_t L, int32_t H, int32_
                                  float* scratch_minmax, uint8_t* out_mask, void* stream) {
   FGVC_CHECK_ARG(maps && scratch_minmax && out_mask && L > 0 && L <= 255 && H > 0 && W > 0 && out_h > 0 && out_w > 0,
                  "fgvc_decode_masks: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  decode_minmax_kernel<<<L, 256, 0, st>>>(maps, H, W, out_h, out_w, scratch_minmax);
-  FGVC_LAUNCH_CHECK();
-  decode_argmax_kernel<<<cdiv(out_h * out_w, 256), 256, 0, st>>>(maps, L, H, W, out_h, out_w, scratch_minmax,
-                                                                 out_mask);
-  FGVC_LAUNCH_CHECK();
-  return FGVC_OK;
+  return launch_decode(maps, false, L, L, H, W, out_h, out_w, reinterpret_cast<uint32_t*>(scratch_minmax), out_mask,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int32_t Lp, int32_t L, int32_t H,
+                                          int32_t W, int32_t out_h, int32_t out_w, float* scratch_minmax,
+                                          uint8_t* out_mask, void* stream) {
+  FGVC_CHECK_ARG(lab_bank && scratch_minmax && out_mask && L > 0 && L <= 255 && Lp >= L && H > 0 && W > 0 &&
+                     out_h > 0 && out_w > 0, "fgvc_decode_masks_pixmajor: bad arguments");
+  return launch_decode(lab_bank + (int64_t)slot * H * W * Lp, true, L, Lp, H, W, out_h, out_w,
+                       reinterpret_cast<uint32_t*>(scratch_minmax), out_mask, (cudaStream_t)stream);
 }

@@ -20,17 +20,26 @@
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers
 // (MMA <-> epilogue).  A 128 x N fp32 tile costs N*128*4 B of TMEM reads and no HBM.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace fgvc {
 
-constexpr int TC_STAGES = 3;
-constexpr int TC_STAGE_BYTES = 64 * 1024;        // A_hi 16K | A_lo 16K | B_hi <=16K | B_lo <=16K
+// Two operand-staging modes:
+//  RES = true  (C <= 256, the normal case): the query tile's hi part stays RESIDENT in shared
+//               memory for the whole CTA (C*512 B) and its lo part lives in TENSOR MEMORY
+//               (C columns, written once with tcgen05.st; the lo*hi product is a TS-form MMA),
+//               so only key boxes stream through the ring: 256 B per key per 32 channels, half
+//               the L2->SM traffic of the streaming mode, which was the measured limiter.
+//  RES = false (C > 256): query hi/lo chunks are re-streamed with every key box.
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MAX_BH = 8;                     // N <= 128 (two accumulators = 256 TMEM columns)
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_TMEM_COLS = 512;                // [0,256) accumulators, [256,256+C) query lo (RES)
+constexpr int TC_ALO_COL = 256;
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*barriers, tables*/ + 1024 /*align*/;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_SMEM_AUX = 1024;                // barriers, tables
 
 struct TcParams {
   int H, W, C, n_pix;
@@ -43,6 +52,7 @@ struct TcParams {
   const int32_t* mem_feat;
   float* tv;
   int32_t* ti;
+  int n_stages, stage_bytes, a_bytes;   // ring geometry (host-chosen)
   float* dbg;                // optional raw affinity dump [box][128][128]
   int32_t* dbg_meta;         // [box][4] = (mem entry, by, bx, N)
   int dbg_max_boxes;
@@ -102,6 +112,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with A taken from tensor memory (TS form): A[128 lanes][K=8 columns] at a_tmem
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4& a, const float4& b, const float4& c,
+                                          const float4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y),
+        "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -158,18 +187,22 @@ __device__ __forceinline__ bool box_skipped(const TcParams& p, const Walk& w, in
   return !in_mask(dy, dx, p.radius, p.mode);
 }
 
-template <int K>
+template <int K, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                        const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tfull_bar = empty_bar + TC_STAGES;    // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+                        const float* __restrict__ bank, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: [query hi, RES only: a_bytes][ring: n_stages * stage_bytes][aux]
+  uint8_t* ring = smem + p.a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint64_t* a_bar = tempty_bar + 2;                  // query hi landed (RES)
+  uint64_t* alo_bar = a_bar + 1;                     // query lo written to TMEM (RES)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(alo_bar + 1);
   int* halfw = reinterpret_cast<int*>(tmem_slot + 4);   // [reach+1] <= 128 entries
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();   // 128B swizzle needs a 1024-aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qy0 = (blockIdx.x / p.tiles_x) * p.QH, qx0 = (blockIdx.x % p.tiles_x) * p.QW;
@@ -186,8 +219,10 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4); }
+    mbar_init(a_bar, 1);
+    mbar_init(alo_bar, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -215,6 +250,11 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (RES && e_lo < e_hi) {      // the query tile's hi part: loaded once, resident
+        mbar_expect_tx(a_bar, (uint32_t)p.a_bytes);
+        for (int kc = 0; kc < n_kc; ++kc)
+          tma_load_5d(&tmap_q, a_bar, smem + kc * 16384, kc * 32, qx0, qy0, 0, job.q_slot);
+      }
       for (int e = e_lo; e < e_hi; ++e) {
         const int raw = p.mem_feat[e];
         const int slot = raw & ~FGVC_MEM_UNMASKED;
@@ -224,13 +264,19 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
             for (int kc = 0; kc < n_kc; ++kc) {
               mbar_wait(empty_bar + stage, phase ^ 1);
-              uint8_t* st = smem + stage * TC_STAGE_BYTES;
-              mbar_expect_tx(full_bar + stage, 2u * 16384u + 2u * b_bytes);
-              tma_load_5d(&tmap_q, full_bar + stage, st, kc * 32, qx0, qy0, 0, job.q_slot);
-              tma_load_5d(&tmap_q, full_bar + stage, st + 16384, kc * 32, qx0, qy0, 1, job.q_slot);
-              tma_load_5d(&tmap_k, full_bar + stage, st + 32768, kc * 32, bx, by, 0, slot);
-              tma_load_5d(&tmap_k, full_bar + stage, st + 49152, kc * 32, bx, by, 1, slot);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              uint8_t* st = ring + stage * p.stage_bytes;
+              if (RES) {
+                mbar_expect_tx(full_bar + stage, 2u * b_bytes);
+                tma_load_5d(&tmap_k, full_bar + stage, st, kc * 32, bx, by, 0, slot);
+                tma_load_5d(&tmap_k, full_bar + stage, st + 16384, kc * 32, bx, by, 1, slot);
+              } else {
+                mbar_expect_tx(full_bar + stage, 2u * 16384u + 2u * b_bytes);
+                tma_load_5d(&tmap_q, full_bar + stage, st, kc * 32, qx0, qy0, 0, job.q_slot);
+                tma_load_5d(&tmap_q, full_bar + stage, st + 16384, kc * 32, qx0, qy0, 1, job.q_slot);
+                tma_load_5d(&tmap_k, full_bar + stage, st + 32768, kc * 32, bx, by, 0, slot);
+                tma_load_5d(&tmap_k, full_bar + stage, st + 49152, kc * 32, bx, by, 1, slot);
+              }
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
       }
@@ -242,6 +288,12 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const uint32_t idesc = make_idesc(128, N);
       int stage = 0, buf = 0;
       uint32_t phase = 0, tphase[2] = {0, 0};
+      if (RES && e_lo < e_hi) {
+        mbar_wait(a_bar, 0);
+        mbar_wait(alo_bar, 0);
+        tc_fence_after();
+      }
+      const uint32_t a_res = smem_u32(smem);
       for (int e = e_lo; e < e_hi; ++e) {
         const int raw = p.mem_feat[e];
         const Walk w = make_walk(p, raw, qy0, qx0);
@@ -254,18 +306,31 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int kc = 0; kc < n_kc; ++kc) {
               mbar_wait(full_bar + stage, phase);
               tc_fence_after();
-              const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-              const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + 16384);
-              const uint64_t b_hi = make_desc(sa + 32768), b_lo = make_desc(sa + 49152);
+              const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
+              if (RES) {
+                const uint64_t a_hi = make_desc(a_res + kc * 16384);
+                const uint64_t b_hi = make_desc(sa), b_lo = make_desc(sa + 16384);
+                const uint32_t a_lo = tmem_base + TC_ALO_COL + kc * 32;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 8 tf32 = 32 B) per 128 B swizzle row
-                const uint64_t o = (uint64_t)(ks * 2);  // +32 B in the >>4 start-address field
-                umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kc | ks) != 0);
-                umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
-                umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+                for (int ks = 0; ks < 4; ++ks) {     // 4 x (K = 8 tf32 = 32 B) per 128 B swizzle row
+                  const uint64_t o = (uint64_t)(ks * 2);
+                  umma_tf32_ts(d_tmem, a_lo + ks * 8, b_hi + o, idesc, (kc | ks) != 0);
+                  umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
+                  umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+                }
+              } else {
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + 16384);
+                const uint64_t b_hi = make_desc(sa + 32768), b_lo = make_desc(sa + 49152);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t o = (uint64_t)(ks * 2);  // +32 B in the >>4 start-address field
+                  umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kc | ks) != 0);
+                  umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
+                  umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+                }
               }
               umma_commit(empty_bar + stage);         // smem slot free once these MMAs retire
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(tfull_bar + buf);             // accumulator complete
             tphase[buf] ^= 1;
@@ -280,6 +345,22 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int m = lg * 32 + lane;                     // query row in the tile
     const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
     const bool qvalid = qy < p.H && qx < p.W;
+    if (RES && e_lo < e_hi) {
+      // query lo part -> tensor memory: lane = query row, column TC_ALO_COL + channel
+      const float4* src = reinterpret_cast<const float4*>(
+          bank + ((int64_t)job.q_slot * 2 + 1) * p.n_pix * p.C + (int64_t)(qvalid ? qy * p.W + qx : 0) * p.C);
+      const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + TC_ALO_COL;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < p.C; c += 16) {
+        float4 a = z, b = z, c4 = z, d = z;
+        if (qvalid) { a = __ldg(src + c / 4); b = __ldg(src + c / 4 + 1); c4 = __ldg(src + c / 4 + 2); d = __ldg(src + c / 4 + 3); }
+        tmem_st16(ta + c, a, b, c4, d);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(alo_bar);
+    }
     TopK<K> top;
     top.init();
     int buf = 0;
@@ -410,11 +491,12 @@ static int pick_bh(int rows) {
   return best;
 }
 
-template <int K>
-static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const TcParams& p, dim3 grid, cudaStream_t st) {
-  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 TC_SMEM_BYTES));
-  affinity_topk_tc_kernel<K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mk, p);
+template <int K, bool RES>
+static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const float* bank, const TcParams& p, dim3 grid,
+                     cudaStream_t st) {
+  const int smem = p.a_bytes + p.n_stages * p.stage_bytes + TC_SMEM_AUX;
+  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_tc_kernel<K, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  affinity_topk_tc_kernel<K, RES><<<grid, TC_THREADS, smem, st>>>(mq, mk, bank, p);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }
@@ -446,9 +528,24 @@ int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C,
   rc = make_map(&mk, bank, n_slots, H, W, C, 16, p.BH);
   if (rc) return rc;
   dim3 grid(cdiv(H, p.QH) * p.tiles_x, groups, n_jobs);
-  if (K <= 4) return launch_tc<4>(mq, mk, p, grid, st);
-  if (K <= 10) return launch_tc<10>(mq, mk, p, grid, st);
-  return launch_tc<16>(mq, mk, p, grid, st);
+  static const bool force_stream = getenv("FGVC_TC_STREAM") != nullptr;   // debugging aid
+  const bool res = C <= 256 && !force_stream;
+  if (res) {
+    p.a_bytes = C * 512;
+    p.stage_bytes = 32 * 1024;
+  } else {
+    p.a_bytes = 0;
+    p.stage_bytes = 64 * 1024;
+  }
+  p.n_stages = min(TC_MAX_STAGES, (TC_SMEM_LIMIT - TC_SMEM_AUX - p.a_bytes) / p.stage_bytes);
+  if (res) {
+    if (K <= 4) return launch_tc<4, true>(mq, mk, bank, p, grid, st);
+    if (K <= 10) return launch_tc<10, true>(mq, mk, bank, p, grid, st);
+    return launch_tc<16, true>(mq, mk, bank, p, grid, st);
+  }
+  if (K <= 4) return launch_tc<4, false>(mq, mk, bank, p, grid, st);
+  if (K <= 10) return launch_tc<10, false>(mq, mk, bank, p, grid, st);
+  return launch_tc<16, false>(mq, mk, bank, p, grid, st);
 }
 
 }  // namespace fgvc

@@ -230,17 +230,20 @@ class MaskClipPropagator:
         self.masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=device)
         self.scratch = torch.empty(2 * L, dtype=torch.float32, device=device)
         self.k1_events = None
+        self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 
     def _decode(self, t):
-        call("fgvc_decode_masks", ptr(self.maps[t]), self.L, self.H, self.W, self.out_hw[0], self.out_hw[1],
-             ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
+        call("fgvc_decode_masks_pixmajor", ptr(self.labels.buf), t, self.labels.Lp, self.L, self.H, self.W,
+             self.out_hw[0], self.out_hw[1], ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
 
-    def run(self, feats, onehot0, events=False):
-        """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks)."""
+    def run(self, feats, onehot0, events=False, want_maps=True):
+        """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks);
+        ``want_maps=False`` skips the NCHW copies of the propagated label maps."""
         cfg = self.cfg
         self.bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
         self.labels.put_nchw(onehot0, 0)
-        self.maps[0].copy_(onehot0)
+        if want_maps:
+            self.maps[0].copy_(onehot0)
         self._decode(0)
         if self.T > 1:
             if events:
@@ -251,8 +254,10 @@ class MaskClipPropagator:
             if events:
                 e1.record()
                 self.k1_events = (e0, e1)
-        for t in range(1, self.T):
-            gather_labels(self.lists, self.table, t - 1, t, self.labels, cfg["temperature"])
-            self.labels.get_nchw(t, out=self.maps[t])
-            self._decode(t)
-        return self.maps, self.masks
+            jobs, _, mem_label = self.table.device(self.device)
+            call("fgvc_mask_clip_tail", ptr(self.lists.val), ptr(self.lists.idx), self.lists.K, self.groups,
+                 ptr(jobs), ptr(self.jobs_host), len(self.table), ptr(mem_label), self.H, self.W,
+                 float(cfg["temperature"]), ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
+                 self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None,
+                 stream_ptr())
+        return (self.maps if want_maps else None), self.masks

@@ -112,18 +112,22 @@ class VanillaTracker(nn.Module):
         else:
             lists = engine.affinity_topk(bank, table, (nr // 2) if nr is not None else 1, cfg.topk,
                                          cfg.get("mask_mode", "circle"), engine=self.engine_id)
+        jobs_dev, _, mem_label = table.device(dev) if len(table) else (None, None, None)
+        jobs_host = torch.tensor(table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
         for (j0, t0), (_, pts) in zip(spans, groups):
             P = pts.shape[0]
             pts = pts.to(device=dev, dtype=torch.float32)
             labels = LabelBank(T, P, Hf, Wf, dev)
             labels.put_gaussians(pts, t0, stride)
-            traj = torch.zeros(T, P, 2, dtype=torch.float64, device=dev)
-            traj[t0] = engine.gaussian_coords(pts, (h, w)).double()
-            for t in range(t0 + 1, T):
-                j = j0 + (t - t0 - 1)
-                engine.gather_labels(lists, table, j, j + 1, labels, cfg.temperature)
-                traj[t] = engine.heatmap_coords(labels.get_nchw(t), (h, w)).double()
-            outs.append(traj)
+            coords = torch.zeros(T, P, 2, dtype=torch.float32, device=dev)
+            coords[t0] = engine.gaussian_coords(pts, (h, w))
+            if T - t0 > 1:
+                scratch = torch.empty(P, Hf, Wf, dtype=torch.float32, device=dev)
+                _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
+                          _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
+                          float(cfg.temperature), _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
+                          _lib.ptr(coords), _lib.stream_ptr())
+            outs.append(coords.double())
         return outs
 
     def forward_test(self, rgbs, query_points, trajectories, visibilities, save_image=False, save_path=None,

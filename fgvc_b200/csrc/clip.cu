@@ -8,15 +8,16 @@ using namespace fgvc;
 // After K0 + K1 ran for the whole clip: for every job j (in order) gather the labels of its
 // query frame (K1b) and decode them to a uint8 mask of the image size.
 extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
-                                   const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t n_jobs,
-                                   const int32_t* mem_label_slot, int32_t H, int32_t W, float temperature,
+                                   const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
+                                   int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
+                                   float temperature,
                                    float* lab_bank, int32_t Lp, int32_t L, int32_t out_h, int32_t out_w,
                                    float* scratch_minmax, uint8_t* masks, float* maps_nchw, void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && masks && scratch_minmax && lab_bank, "fgvc_mask_clip_tail: null pointer");
   FGVC_CHECK_ARG(L > 0 && L <= 255 && Lp >= L && Lp % 4 == 0, "fgvc_mask_clip_tail: bad label sizes");
   const int n_pix = H * W;
   const int64_t mask_elems = (int64_t)out_h * out_w;
-  for (int j = 0; j < n_jobs; ++j) {
+  for (int j = job_begin; j < job_end; ++j) {
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
                                 temperature, lab_bank, Lp, stream);
     if (rc) return rc;

@@ -126,8 +126,9 @@ class TopKLists:
         self.idx = torch.empty(n_jobs, groups, n_query, K, dtype=torch.int32, device=device)
 
 
-def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None):
-    """K1 over every job of ``table`` in one launch."""
+def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
+                  job_range=None):
+    """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch."""
     dev = bank.buf.device
     jobs, mem_feat, _ = table.device(dev)
     if groups is None:
@@ -136,8 +137,12 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
         lists = TopKLists(len(table), groups, bank.H * bank.W, K, dev)
     assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
-    call("fgvc_affinity_topk", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C, ptr(jobs), len(table), ptr(mem_feat),
-         int(radius), mode, int(K), int(groups), ptr(lists.val), ptr(lists.idx), int(engine), stream_ptr())
+    j0, j1 = job_range if job_range is not None else (0, len(table))
+    per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
+    call("fgvc_affinity_topk", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C,
+         ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
+         ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),
+         int(engine), stream_ptr())
     return lists
 
 
@@ -236,6 +241,18 @@ class MaskClipPropagator:
         call("fgvc_decode_masks_pixmajor", ptr(self.labels.buf), t, self.labels.Lp, self.L, self.H, self.W,
              self.out_hw[0], self.out_hw[1], ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
 
+    def _tail(self, j0, j1, want_maps):
+        jobs, _, mem_label = self.table.device(self.device)
+        call("fgvc_mask_clip_tail", ptr(self.lists.val), ptr(self.lists.idx), self.lists.K, self.groups,
+             ptr(jobs), ptr(self.jobs_host), j0, j1, ptr(mem_label), self.H, self.W,
+             float(self.cfg["temperature"]), ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
+             self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None, stream_ptr())
+
+    def _k1(self, j0, j1):
+        cfg = self.cfg
+        affinity_topk(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
+                      groups=self.groups, engine=self.engine_id, lists=self.lists, job_range=(j0, j1))
+
     def run(self, feats, onehot0, events=False, want_maps=True):
         """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks);
         ``want_maps=False`` skips the NCHW copies of the propagated label maps."""
@@ -249,15 +266,42 @@ class MaskClipPropagator:
             if events:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            affinity_topk(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
-                          groups=self.groups, engine=self.engine_id, lists=self.lists)
+            self._k1(0, len(self.table))
             if events:
                 e1.record()
                 self.k1_events = (e0, e1)
-            jobs, _, mem_label = self.table.device(self.device)
-            call("fgvc_mask_clip_tail", ptr(self.lists.val), ptr(self.lists.idx), self.lists.K, self.groups,
-                 ptr(jobs), ptr(self.jobs_host), len(self.table), ptr(mem_label), self.H, self.W,
-                 float(cfg["temperature"]), ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
-                 self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None,
-                 stream_ptr())
+            self._tail(0, len(self.table), want_maps)
         return (self.maps if want_maps else None), self.masks
+
+    def run_host(self, feats_host, onehot_host, masks_host, chunk_frames=8):
+        """End-to-end form: PINNED host features [T,C,H,W] / one-hot [L,H,W] in, uint8 masks
+        [T,h,w] out to pinned host memory.  The host->device copy of frame chunk i+1 (copy
+        stream) overlaps K0 + K1 + tail of chunk i: a frame's jobs only need earlier frames."""
+        cfg = self.cfg
+        if not hasattr(self, "_stage"):
+            self._stage = torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
+            self._onehot = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
+            self._copy = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream()
+        self._copy.wait_stream(cur)                       # staging buffers free again
+        evs = []
+        with torch.cuda.stream(self._copy):
+            self._onehot.copy_(onehot_host, non_blocking=True)
+            for s in range(0, self.T, chunk_frames):
+                e = min(self.T, s + chunk_frames)
+                self._stage[s:e].copy_(feats_host[s:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy)
+                evs.append((s, e, ev))
+        for s, e, ev in evs:
+            cur.wait_event(ev)
+            self.bank.load_frames(self._stage[s:e], s, normalize=cfg.get("with_norm", True))
+            if s == 0:
+                self.labels.put_nchw(self._onehot, 0)
+                self._decode(0)
+            j0, j1 = max(s, 1) - 1, e - 1                 # job t-1 propagates frame t
+            if j1 > j0:
+                self._k1(j0, j1)
+                self._tail(j0, j1, False)
+        masks_host.copy_(self.masks, non_blocking=True)
+        return masks_host

@@ -157,15 +157,16 @@ FGVC_API int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int
 /* Clip-level tails: the sequential part of the reference loop (vanilla_tracker.py:345-412)
  * enqueued by one call after K0 + K1 ran for the whole clip.  jobs_host = host copy of the
  * job table (the launcher needs each out_slot).
- *  mask tail : per job K1b gather -> [optional NCHW copy into maps_nchw[slot]] -> decode into
+ *  mask tail : per job in [job_begin, job_end) K1b gather -> [optional NCHW copy into maps_nchw[slot]] -> decode into
  *              masks[slot][out_h][out_w];
  *  point tail: per job in [job_begin, job_end) K1b gather -> NCHW (maps_scratch [L][H*W]) ->
  *              K3 into coords[slot][L][2]. */
 FGVC_API int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
-                        const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t n_jobs,
-                        const int32_t* mem_label_slot, int32_t H, int32_t W, float temperature,
-                        float* lab_bank, int32_t Lp, int32_t L, int32_t out_h, int32_t out_w,
-                        float* scratch_minmax, uint8_t* masks, float* maps_nchw, void* stream);
+                        const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
+                        int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
+                        float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
+                        int32_t out_w, float* scratch_minmax, uint8_t* masks, float* maps_nchw,
+                        void* stream);
 FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                          const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                          int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,

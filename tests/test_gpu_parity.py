@@ -372,3 +372,70 @@ def test_mask_propagation_argmax_agreement():
         want = O.decode_masks_port(labels[t], (480, 854))
         agree = float((masks[t].cpu().long() == want).float().mean())
         assert agree >= 0.999, (t, agree)
+
+
+def test_clip_host_pipeline_equals_resident_run():
+    """The end-to-end path (pinned host buffers, chunked copies overlapping K0/K1/tail per
+    chunk) must give bit-identical masks to the one-launch resident path."""
+    from fgvc_b200 import engine
+    g = torch.Generator().manual_seed(11)
+    T, C, H, W, L = 11, 64, 20, 28, 5
+    feats = _coherent(g, T, C, H, W)
+    seg = (torch.arange(H).view(-1, 1) // 7 + (torch.arange(W).view(1, -1) // 15) * 3).clamp(max=L - 1)
+    onehot = torch.nn.functional.one_hot(seg, L).permute(2, 0, 1).float().contiguous()
+    cfg = dict(precede_frames=4, topk=10, temperature=0.07, neighbor_range=10, with_first=True, with_first_neighbor=True)
+    clip = engine.MaskClipPropagator(T, C, H, W, L, (80, 112), cfg, torch.device("cuda"))
+    maps, masks = clip.run(feats.cuda(), onehot.cuda())
+    want = masks.clone()
+    want_maps = maps.clone()
+    out = torch.empty(T, 80, 112, dtype=torch.uint8).pin_memory()
+    clip.run_host(feats.pin_memory(), onehot.pin_memory(), out, chunk_frames=3)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want.cpu())
+    # and the label maps agree with the oracle driver loop
+    labels = [onehot]
+    mask = O.neighbor_mask(H, W, 10)
+    for t in range(1, T):
+        mem = O.memory_frames(t, 4)
+        kk = feats[mem].permute(1, 0, 2, 3)[None]
+        vv = torch.stack([labels[m] for m in mem], dim=1)[None]
+        labels.append(O.propagate_port(feats[t][None], kk, vv, mask=mask, temperature=0.07, topk=10)[0])
+    err = (want_maps.cpu() - torch.stack(labels)).abs().amax(dim=1)
+    assert float((err > TOL).float().mean()) <= 2e-3
+
+
+def test_raw_c_abi_as_in_integration_md():
+    """the C ABI driven with nothing but ctypes + device pointers."""
+    import ctypes
+    import fgvc_b200
+    from fgvc_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.fgvc_last_error.restype = ctypes.c_char_p
+    P = ctypes.c_void_p
+    T, C, H, W, L, K = 3, 64, 20, 27, 8, 10
+    g = torch.Generator().manual_seed(12)
+    feats = _coherent(g, T + 1, C, H, W).cuda()
+    v = torch.rand(1, L, T, H, W, generator=g).cuda()
+    bank = torch.empty(T + 1, 2, H * W, C, device="cuda")
+    labels = torch.zeros(T + 1, H * W, 8, device="cuda")
+    labels[:T] = v[0].permute(1, 2, 3, 0).reshape(T, H * W, L)
+    st = P(torch.cuda.current_stream().cuda_stream)
+    rc = lib.fgvc_prep_features(P(feats.data_ptr()), ctypes.c_int64(C * H * W), ctypes.c_int64(H * W), T + 1, C, H, W,
+                                1, P(bank.data_ptr()), 0, st)
+    assert rc == 0, lib.fgvc_last_error()
+    jobs = torch.tensor([[T, 0, T, T]], dtype=torch.int32, device="cuda")
+    mem_feat = torch.arange(T, dtype=torch.int32, device="cuda")
+    mem_lab = torch.arange(T, dtype=torch.int32, device="cuda")
+    val = torch.empty(1, 1, H * W, K, device="cuda")
+    idx = torch.empty(1, 1, H * W, K, dtype=torch.int32, device="cuda")
+    rc = lib.fgvc_affinity_topk(P(bank.data_ptr()), T + 1, H, W, C, P(jobs.data_ptr()), 1, P(mem_feat.data_ptr()),
+                                5, 0, K, 1, P(val.data_ptr()), P(idx.data_ptr()), 0, st)
+    assert rc == 0, lib.fgvc_last_error()
+    rc = lib.fgvc_gather_labels(P(val.data_ptr()), P(idx.data_ptr()), K, 1, P(jobs.data_ptr()), 0, 1,
+                                P(mem_lab.data_ptr()), H * W, ctypes.c_float(0.07), P(labels.data_ptr()), 8, st)
+    assert rc == 0, lib.fgvc_last_error()
+    torch.cuda.synchronize()
+    got = labels[T].t().reshape(1, L, H, W)
+    want = fgvc_b200.masked_attention_efficient_v2(feats[T][None], feats[:T].permute(1, 0, 2, 3)[None].contiguous(),
+                                                   v, 5, temperature=0.07, topk=K)
+    assert torch.equal(got, want)

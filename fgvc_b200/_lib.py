@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libfgvc_b200.so")
 
 MASK_CIRCLE, MASK_SQUARE = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+BANK_TF32, BANK_F16 = 0, 1
 MEM_UNMASKED = 0x40000000
 
 
@@ -34,14 +35,14 @@ SIGNATURES = {
     "fgvc_version": (I, []),
     "fgvc_device_count": (I, []),
     "fgvc_launch_count": (L64, []),
-    "fgvc_prep_features": (I, [P, L64, L64, I, I, I, I, I, P, I, P]),
+    "fgvc_prep_features": (I, [P, L64, L64, I, I, I, I, I, P, I, I, P]),
     "fgvc_labels_to_pixmajor": (I, [P, L64, I, I, P, I, I, P]),
     "fgvc_labels_to_nchw": (I, [P, I, I, I, I, P, P]),
     "fgvc_gaussian_labels": (I, [P, I, I, I, I, F, P, I, I, P]),
-    "fgvc_tc_supported": (I, [I, I, I, I]),
+    "fgvc_tc_supported": (I, [I, I, I, I, I]),
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
-    "fgvc_affinity_topk": (I, [P, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
-    "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
+    "fgvc_affinity_topk": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
+    "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
     "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, P, I, P]),
     "fgvc_heatmap_coords": (I, [P, I, I, I, I, I, I, P, P]),
     "fgvc_gaussian_coords": (I, [P, I, I, I, F, I, P, P]),
@@ -49,7 +50,7 @@ SIGNATURES = {
     "fgvc_decode_masks_pixmajor": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, P, P, P, P]),
     "fgvc_point_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, I, P, P, P]),
-    "fgvc_c2f_propagate": (I, [P, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
+    "fgvc_c2f_propagate": (I, [P, I, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
 }
 
 _lib = None

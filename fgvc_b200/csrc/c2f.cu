@@ -13,9 +13,9 @@
 
 namespace fgvc {
 
-template <int K>
+template <int K, int FMT>
 __global__ void __launch_bounds__(256)
-c2f_fine_kernel(const float* __restrict__ fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
+c2f_fine_kernel(const void* __restrict__ fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
                 fgvc_job job, const int32_t* __restrict__ mem_feat, const int32_t* __restrict__ mem_label,
                 const int32_t* __restrict__ best_idx, int rf, int k_out, float temperature,
                 const float* __restrict__ fine_lab, int Lp, float* __restrict__ out) {
@@ -28,12 +28,9 @@ c2f_fine_kernel(const float* __restrict__ fine_bank, int Hc, int Wc, int Hf, int
   const int qy = q / Wc, qx = q - qy * Wc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nf = Hf * Wf, nc = Hc * Wc;
-  const int64_t slot_floats = feat_slot_floats(nf, Cf);
-  {
-    const float* hi = fine_bank + (int64_t)job.q_slot * slot_floats + (int64_t)((qy * scale) * Wf + qx * scale) * Cf;
-    const float* lo = hi + (int64_t)nf * Cf;
-    for (int c = tid; c < Cf; c += 256) qf[c] = __ldg(hi + c) + __ldg(lo + c);
-  }
+  for (int c4 = tid; c4 < Cf / 4; c4 += 256)
+    *reinterpret_cast<float4*>(qf + 4 * c4) =
+        bank_load4<FMT>(fine_bank, job.q_slot, nf, Cf, (qy * scale) * Wf + qx * scale, c4);
   __syncthreads();
   const int R = 2 * rf + 1;
   const int n_mem = job.mem_end - job.mem_begin;
@@ -44,20 +41,16 @@ c2f_fine_kernel(const float* __restrict__ fine_bank, int Hc, int Wc, int Hf, int
     const int slot = __ldg(mem_feat + job.mem_begin + t) & ~FGVC_MEM_UNMASKED;
     const int b = max(__ldg(best_idx + (int64_t)t * nc + q), 0) % nc;   // coarse arg-max key pixel
     const int cy = (b / Wc) * scale, cx = (b % Wc) * scale;
-    const float* hi = fine_bank + (int64_t)slot * slot_floats;
-    const float* lo = hi + (int64_t)nf * Cf;
     for (int w = warp; w < R * R; w += 8) {
       int dy = w / R - rf, dx = w % R - rf;
       int y = cy + dy, x = cx + dx;
       float dot = 0.f;
       if (y >= 0 && y < Hf && x >= 0 && x < Wf) {
-        const float4* h4 = reinterpret_cast<const float4*>(hi + (int64_t)(y * Wf + x) * Cf);
-        const float4* l4 = reinterpret_cast<const float4*>(lo + (int64_t)(y * Wf + x) * Cf);
         for (int c = lane; c < c4n; c += 32) {
-          float4 a = __ldg(h4 + c), bb = __ldg(l4 + c);
+          float4 a = bank_load4<FMT>(fine_bank, slot, nf, Cf, y * Wf + x, c);
           float4 qq = *reinterpret_cast<const float4*>(qf + 4 * c);
-          dot = fmaf(a.x + bb.x, qq.x, dot); dot = fmaf(a.y + bb.y, qq.y, dot);
-          dot = fmaf(a.z + bb.z, qq.z, dot); dot = fmaf(a.w + bb.w, qq.w, dot);
+          dot = fmaf(a.x, qq.x, dot); dot = fmaf(a.y, qq.y, dot);
+          dot = fmaf(a.z, qq.z, dot); dot = fmaf(a.w, qq.w, dot);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -119,12 +112,12 @@ c2f_fine_kernel(const float* __restrict__ fine_bank, int Hc, int Wc, int Hf, int
   }
 }
 
-template <int K>
-static int launch_fine(const float* fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
+template <int K, int FMT>
+static int launch_fine(const void* fine_bank, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
                        const fgvc_job& job, const int32_t* mem_feat, const int32_t* mem_label,
                        const int32_t* best, int rf, int k_out, float temperature, const float* fine_lab, int Lp,
                        float* out, cudaStream_t st) {
-  c2f_fine_kernel<K><<<Hc * Wc, 256, Cf * sizeof(float), st>>>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, job,
+  c2f_fine_kernel<K, FMT><<<Hc * Wc, 256, Cf * sizeof(float), st>>>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, job,
                                                                mem_feat, mem_label, best, rf, k_out, temperature,
                                                                fine_lab, Lp, out);
   FGVC_LAUNCH_CHECK();
@@ -135,8 +128,8 @@ static int launch_fine(const float* fine_bank, int Hc, int Wc, int Hf, int Wf, i
 
 using namespace fgvc;
 
-extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t n_slots, int32_t Hc, int32_t Wc, int32_t C,
-                                  const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
+extern "C" int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, int32_t n_slots, int32_t Hc, int32_t Wc,
+                                  int32_t C, const void* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
                                   const fgvc_job* job_dev, const fgvc_job* job_host, const int32_t* mem_feat_slot,
                                   const int32_t* mem_label_slot, int32_t radius, int32_t mask_mode,
                                   int32_t radius_fine, int32_t K, float temperature, const float* fine_lab_bank,
@@ -151,12 +144,21 @@ extern "C" int fgvc_c2f_propagate(const float* coarse_bank, int32_t n_slots, int
   const int n_mem = job_host->mem_end - job_host->mem_begin;
   FGVC_CHECK_ARG(n_mem >= 1 && n_mem <= 64, "fgvc_c2f_propagate: memory length %d not in [1,64]", n_mem);
   // coarse stage: top-1 per memory frame == groups = n_mem
-  int rc = fgvc_affinity_topk(coarse_bank, n_slots, Hc, Wc, C, job_dev, 1, mem_feat_slot, radius, mask_mode, 1, n_mem,
+  int rc = fgvc_affinity_topk(coarse_bank, bank_format, n_slots, Hc, Wc, C, job_dev, 1, mem_feat_slot, radius, mask_mode, 1, n_mem,
                               scratch_val, scratch_idx, engine, stream);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int scale = Hf / Hc;
-  if (K <= 4) return launch_fine<4>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
-  if (K <= 10) return launch_fine<10>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
-  return launch_fine<16>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, mem_label_slot, scratch_idx, radius_fine, K, temperature, fine_lab_bank, Lp, out, st);
+#define FGVC_FINE(KK)                                                                                              \
+  return bank_format == FGVC_BANK_TF32                                                                             \
+             ? launch_fine<KK, FGVC_BANK_TF32>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot,      \
+                                               mem_label_slot, scratch_idx, radius_fine, K, temperature,            \
+                                               fine_lab_bank, Lp, out, st)                                          \
+             : launch_fine<KK, FGVC_BANK_F16>(fine_bank, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot,       \
+                                              mem_label_slot, scratch_idx, radius_fine, K, temperature,             \
+                                              fine_lab_bank, Lp, out, st)
+  if (K <= 4) { FGVC_FINE(4); }
+  if (K <= 10) { FGVC_FINE(10); }
+  FGVC_FINE(16);
+#undef FGVC_FINE
 }

@@ -33,16 +33,21 @@ extern "C" int fgvc_device_count(void) {
   return n;
 }
 
-extern "C" int fgvc_tc_supported(int32_t H, int32_t W, int32_t C, int32_t K) { return tc_supported(H, W, C, K) ? 1 : 0; }
+static bool tc_ok(int fmt, int H, int W, int C, int K) {
+  return fmt == FGVC_BANK_F16 ? tc16_supported(H, W, C, K) : tc_supported(H, W, C, K);
+}
+extern "C" int fgvc_tc_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K) {
+  return tc_ok(bank_format, H, W, C, K) ? 1 : 0;
+}
 
 extern "C" int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K) {
   return (int64_t)n_jobs * groups * n_query * K * 4;
 }
 
-static int pick_engine(int engine, int H, int W, int C, int K, bool* use_tc) {
-  bool ok = tc_supported(H, W, C, K);
+static int pick_engine(int engine, int fmt, int H, int W, int C, int K, bool* use_tc) {
+  bool ok = tc_ok(fmt, H, W, C, K);
   if (engine == FGVC_ENGINE_TCGEN05) {
-    FGVC_CHECK_ARG(ok, "tcgen05 engine needs C %% 32 == 0, C <= 512 and K <= 16 (C=%d K=%d)", C, K);
+    FGVC_CHECK_ARG(ok, "tcgen05 engine needs C %% 32 == 0 (TF32 bank) / C %% 64 == 0 (F16 bank) and K <= 16 (C=%d K=%d)", C, K);
     *use_tc = true;
   } else if (engine == FGVC_ENGINE_SIMT) {
     *use_tc = false;
@@ -53,7 +58,7 @@ static int pick_engine(int engine, int H, int W, int C, int K, bool* use_tc) {
   return FGVC_OK;
 }
 
-static int affinity_topk_impl(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+static int affinity_topk_impl(const void* feat_bank, int32_t fmt, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                               const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius,
                               int32_t mask_mode, int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx,
                               int32_t engine, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes, void* stream) {
@@ -63,31 +68,35 @@ static int affinity_topk_impl(const float* feat_bank, int32_t n_slots, int32_t H
   FGVC_CHECK_ARG(groups >= 1 && groups <= 64, "fgvc_affinity_topk: groups=%d not in [1,64]", groups);
   FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk: radius=%d must be >= 1", radius);
   FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk: bad mask mode");
+  FGVC_CHECK_ARG(fmt == FGVC_BANK_TF32 || fmt == FGVC_BANK_F16, "fgvc_affinity_topk: bad bank format %d", fmt);
   bool use_tc = false;
-  int rc = pick_engine(engine, H, W, C, K, &use_tc);
+  int rc = pick_engine(engine, fmt, H, W, C, K, &use_tc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc && fmt == FGVC_BANK_F16)
+    return launch_affinity_topk_tc16(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                                     groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
   if (use_tc)
-    return launch_affinity_topk_tc(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+    return launch_affinity_topk_tc(reinterpret_cast<const float*>(feat_bank), n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
                                    groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
-  return launch_affinity_topk_simt(feat_bank, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
+  return launch_affinity_topk_simt(feat_bank, fmt, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
                                    topk_val, topk_idx, st);
 }
 
-extern "C" int fgvc_affinity_topk(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+extern "C" int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                                   const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius,
                                   int32_t mask_mode, int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx,
                                   int32_t engine, void* stream) {
-  return affinity_topk_impl(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, groups,
-                            topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
+  return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
+                            K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
 }
 
-extern "C" int fgvc_debug_affinity_boxes(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+extern "C" int fgvc_debug_affinity_boxes(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                                          const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                                          int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,
                                          int32_t* topk_idx, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes,
                                          void* stream) {
   FGVC_CHECK_ARG(dbg && dbg_meta && dbg_max_boxes > 0, "fgvc_debug_affinity_boxes: null debug buffers");
-  return affinity_topk_impl(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K, 1,
-                            topk_val, topk_idx, FGVC_ENGINE_TCGEN05, dbg, dbg_meta, dbg_max_boxes, stream);
+  return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                            1, topk_val, topk_idx, FGVC_ENGINE_TCGEN05, dbg, dbg_meta, dbg_max_boxes, stream);
 }

@@ -1,6 +1,7 @@
 // Shared helpers for the fgvc_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
 #include <stdio.h>
@@ -39,8 +40,35 @@ extern std::atomic<long long> g_launches;
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// size in floats of one feature-bank slot: [2][n_pix][C]
+// size in elements of one feature-bank slot: [2][n_pix][C]
 __host__ __device__ inline int64_t feat_slot_floats(int n_pix, int C) { return 2ll * n_pix * C; }
+
+// x = hi + lo * 2^-11 for the fp16 split (hi = fp16(x), lo = fp16((x - hi) * 2^11))
+#define FGVC_F16_LO_SCALE 2048.0f
+#define FGVC_F16_LO_INV (1.0f / 2048.0f)
+
+// 4 consecutive channels of pixel `pix` of slot `slot`, reconstructed to fp32, for either bank format
+template <int FMT>
+__device__ __forceinline__ float4 bank_load4(const void* __restrict__ bank, int slot, int n_pix, int C, int pix, int c4) {
+  if (FMT == FGVC_BANK_TF32) {
+    const float4* hi = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bank) +
+                                                       (int64_t)slot * feat_slot_floats(n_pix, C));
+    const float4* lo = hi + ((int64_t)n_pix * C) / 4;
+    const int64_t o = ((int64_t)pix * C) / 4 + c4;
+    float4 a = __ldg(hi + o), b = __ldg(lo + o);
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  } else {
+    const uint2* hi = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(bank) +
+                                                     (int64_t)slot * feat_slot_floats(n_pix, C));
+    const uint2* lo = hi + ((int64_t)n_pix * C) / 4;
+    const int64_t o = ((int64_t)pix * C) / 4 + c4;
+    uint2 a = __ldg(hi + o), b = __ldg(lo + o);
+    float2 a0 = __half22float2(*reinterpret_cast<__half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<__half2*>(&a.y));
+    float2 b0 = __half22float2(*reinterpret_cast<__half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<__half2*>(&b.y));
+    return make_float4(fmaf(b0.x, FGVC_F16_LO_INV, a0.x), fmaf(b0.y, FGVC_F16_LO_INV, a0.y),
+                       fmaf(b1.x, FGVC_F16_LO_INV, a1.x), fmaf(b1.y, FGVC_F16_LO_INV, a1.y));
+  }
+}
 
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -98,7 +126,7 @@ __device__ __forceinline__ bool in_mask(int dy, int dx, int r, int mode) {
 __host__ __device__ inline int mask_reach(int r, int mode) { return mode == FGVC_MASK_CIRCLE ? r - 1 : r; }
 
 // host launchers implemented in the .cu files -------------------------------------------
-int launch_affinity_topk_simt(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+int launch_affinity_topk_simt(const void* bank, int fmt, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups,
                               float* tv, int32_t* ti, cudaStream_t st);
 int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
@@ -106,6 +134,10 @@ int launch_affinity_topk_tc(const float* bank, int n_slots, int H, int W, int C,
                             float* tv, int32_t* ti, float* dbg, int32_t* dbg_meta, int dbg_max_boxes,
                             cudaStream_t st);
 bool tc_supported(int H, int W, int C, int K);
+bool tc16_supported(int H, int W, int C, int K);
+int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+                              const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
+                              float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st);
 int launch_decode(const float* src, bool pixmajor, int L, int Lp, int H, int W, int out_h, int out_w,
                   uint32_t* minmax, uint8_t* out, cudaStream_t st);
 

@@ -7,9 +7,10 @@ namespace fgvc {
 // Read: for each channel a warp reads 32 consecutive pixels (128 B, coalesced).
 // Write: for each pixel consecutive threads write consecutive channels (coalesced).
 // smem tile[C][33] breaks the transpose bank conflicts.
+template <int FMT>
 __global__ void __launch_bounds__(256)
 prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_t chan_stride, int C,
-                     int n_pix, int normalize, float* __restrict__ bank, int first_slot) {
+                     int n_pix, int normalize, void* __restrict__ bank_v, int first_slot) {
   extern __shared__ float tile[];  // [C][33] + norm[32]
   float* inv = tile + C * 33;
   const int frame = blockIdx.y;
@@ -33,16 +34,25 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
     if (lane == 0) inv[pp] = normalize ? fmaxf(sqrtf(acc), 1e-12f) : 1.f;
   }
   __syncthreads();
-  float* hi = bank + (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
-  float* lo = hi + (int64_t)n_pix * C;
+  const int64_t slot_off = (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
   for (int i = threadIdx.x; i < 32 * C; i += 256) {
     int pp = i / C, c = i - pp * C;
     int p = p0 + pp;
     if (p < n_pix) {
       float x = __fdiv_rn(tile[c * 33 + pp], inv[pp]);
-      float h = tf32_round(x);
-      hi[(int64_t)p * C + c] = h;
-      lo[(int64_t)p * C + c] = x - h;
+      if (FMT == FGVC_BANK_TF32) {
+        float* hi = reinterpret_cast<float*>(bank_v) + slot_off;
+        float* lo = hi + (int64_t)n_pix * C;
+        float h = tf32_round(x);
+        hi[(int64_t)p * C + c] = h;
+        lo[(int64_t)p * C + c] = x - h;
+      } else {
+        __half* hi = reinterpret_cast<__half*>(bank_v) + slot_off;
+        __half* lo = hi + (int64_t)n_pix * C;
+        __half h = __float2half_rn(x);
+        hi[(int64_t)p * C + c] = h;
+        lo[(int64_t)p * C + c] = __float2half_rn((x - __half2float(h)) * FGVC_F16_LO_SCALE);
+      }
     }
   }
 }
@@ -105,20 +115,26 @@ using namespace fgvc;
 
 extern "C" int fgvc_prep_features(const float* src, int64_t src_frame_stride, int64_t src_chan_stride,
                                   int32_t n_frames, int32_t C, int32_t H, int32_t W, int32_t normalize,
-                                  float* feat_bank, int32_t first_slot, void* stream) {
+                                  void* feat_bank, int32_t bank_format, int32_t first_slot, void* stream) {
   FGVC_CHECK_ARG(src && feat_bank, "fgvc_prep_features: null pointer");
   FGVC_CHECK_ARG(n_frames > 0 && C > 0 && H > 0 && W > 0, "fgvc_prep_features: bad shape");
   FGVC_CHECK_ARG(C % 4 == 0 && C <= 1024, "fgvc_prep_features: C=%d must be a multiple of 4, <= 1024", C);
   int n_pix = H * W;
   size_t smem = (size_t)(C * 33 + 32) * sizeof(float);
+  FGVC_CHECK_ARG(bank_format == FGVC_BANK_TF32 || bank_format == FGVC_BANK_F16, "fgvc_prep_features: bad bank format");
   static bool attr_set = false;
   if (!attr_set) {
-    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
   dim3 grid(cdiv(n_pix, 32), n_frames);
-  prep_features_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_frame_stride, src_chan_stride, C,
-                                                                  n_pix, normalize, feat_bank, first_slot);
+  if (bank_format == FGVC_BANK_TF32)
+    prep_features_kernel<FGVC_BANK_TF32><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        src, src_frame_stride, src_chan_stride, C, n_pix, normalize, feat_bank, first_slot);
+  else
+    prep_features_kernel<FGVC_BANK_F16><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        src, src_frame_stride, src_chan_stride, C, n_pix, normalize, feat_bank, first_slot);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }

@@ -15,9 +15,9 @@ namespace fgvc {
 constexpr int TQ = 8;        // query / key tile edge
 constexpr int TP = TQ * TQ;  // 64 pixels
 
-template <int K>
+template <int K, int FMT>
 __global__ void __launch_bounds__(256, 1)
-affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
+affinity_topk_simt_kernel(const void* __restrict__ bank, int H, int W, int C,
                           const fgvc_job* __restrict__ jobs, const int32_t* __restrict__ mem_feat,
                           int radius, int mode, int groups, int k_out, float* __restrict__ tv,
                           int32_t* __restrict__ ti) {
@@ -34,7 +34,6 @@ affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
   const int n_pix = H * W;
   const int tid = threadIdx.x;
   const int c4n = C / 4;
-  const int64_t slot_floats = feat_slot_floats(n_pix, C);
 
   // memory entries of this group
   const int n_mem = job.mem_end - job.mem_begin;
@@ -42,22 +41,13 @@ affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
   const int e_lo = job.mem_begin + g * per;
   const int e_hi = min(job.mem_end, e_lo + per);
 
-  // stage the query tile: x = hi + lo (exact fp32 value)
-  {
-    const float* hi = bank + (int64_t)job.q_slot * slot_floats;
-    const float* lo = hi + (int64_t)n_pix * C;
-    for (int i = tid; i < TP * c4n; i += 256) {
-      int p = i / c4n, c4 = i - p * c4n;
-      int y = qy0 + p / TQ, x = qx0 + p % TQ;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y < H && x < W) {
-        int64_t o = ((int64_t)(y * W + x) * C) / 4 + c4;
-        float4 a = __ldg(reinterpret_cast<const float4*>(hi) + o);
-        float4 b = __ldg(reinterpret_cast<const float4*>(lo) + o);
-        v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      }
-      *reinterpret_cast<float4*>(Qp + p * ld + c4 * 4) = v;
-    }
+  // stage the query tile: x = hi + lo (the fp32 value the split encodes)
+  for (int i = tid; i < TP * c4n; i += 256) {
+    int p = i / c4n, c4 = i - p * c4n;
+    int y = qy0 + p / TQ, x = qx0 + p % TQ;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < H && x < W) v = bank_load4<FMT>(bank, job.q_slot, n_pix, C, y * W + x, c4);
+    *reinterpret_cast<float4*>(Qp + p * ld + c4 * 4) = v;
   }
 
   TopK<K> top;
@@ -71,8 +61,6 @@ affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
     const int raw = mem_feat[e];
     const bool masked = !(raw & FGVC_MEM_UNMASKED);
     const int slot = raw & ~FGVC_MEM_UNMASKED;
-    const float* hi = bank + (int64_t)slot * slot_floats;
-    const float* lo = hi + (int64_t)n_pix * C;
     const int pos_base = (e - job.mem_begin) * n_pix;
     int ky_lo = 0, ky_hi = H - 1, kx_lo = 0, kx_hi = W - 1;
     if (masked) {
@@ -90,12 +78,7 @@ affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
           int p = i / c4n, c4 = i - p * c4n;
           int y = ty0 + p / TQ, x = tx0 + p % TQ;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (y < H && x < W) {
-            int64_t o = ((int64_t)(y * W + x) * C) / 4 + c4;
-            float4 a = __ldg(reinterpret_cast<const float4*>(hi) + o);
-            float4 b = __ldg(reinterpret_cast<const float4*>(lo) + o);
-            v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-          }
+          if (y < H && x < W) v = bank_load4<FMT>(bank, slot, n_pix, C, y * W + x, c4);
           *reinterpret_cast<float4*>(Kp + p * ld + c4 * 4) = v;
         }
         __syncthreads();
@@ -149,28 +132,33 @@ affinity_topk_simt_kernel(const float* __restrict__ bank, int H, int W, int C,
   }
 }
 
-template <int K>
-static int launch_k(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+template <int K, int FMT>
+static int launch_k(const void* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                     const int32_t* mem_feat, int radius, int mode, int k_out, int groups, float* tv,
                     int32_t* ti, cudaStream_t st) {
   size_t smem = (size_t)(2 * TP * (C + 4) + TP * 65) * sizeof(float);
   FGVC_CHECK_ARG(smem <= 227 * 1024, "simt engine: C=%d needs %zu B of shared memory", C, smem);
-  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_simt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_simt_kernel<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   dim3 grid(cdiv(H, TQ) * cdiv(W, TQ), groups, n_jobs);
-  affinity_topk_simt_kernel<K><<<grid, 256, smem, st>>>(bank, H, W, C, jobs, mem_feat, radius, mode, groups,
+  affinity_topk_simt_kernel<K, FMT><<<grid, 256, smem, st>>>(bank, H, W, C, jobs, mem_feat, radius, mode, groups,
                                                        k_out, tv, ti);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }
 
-int launch_affinity_topk_simt(const float* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+int launch_affinity_topk_simt(const void* bank, int fmt, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv,
                               int32_t* ti, cudaStream_t st) {
   FGVC_CHECK_ARG(C % 4 == 0, "simt engine: C=%d must be a multiple of 4", C);
-  if (K <= 4) return launch_k<4>(bank, H, W, C, jobs, n_jobs, mem_feat, radius, mode, K, groups, tv, ti, st);
-  if (K <= 10) return launch_k<10>(bank, H, W, C, jobs, n_jobs, mem_feat, radius, mode, K, groups, tv, ti, st);
-  return launch_k<16>(bank, H, W, C, jobs, n_jobs, mem_feat, radius, mode, K, groups, tv, ti, st);
+#define FGVC_SIMT(KK)                                                                                            \
+  return fmt == FGVC_BANK_TF32                                                                                   \
+             ? launch_k<KK, FGVC_BANK_TF32>(bank, H, W, C, jobs, n_jobs, mem_feat, radius, mode, K, groups, tv, ti, st) \
+             : launch_k<KK, FGVC_BANK_F16>(bank, H, W, C, jobs, n_jobs, mem_feat, radius, mode, K, groups, tv, ti, st)
+  if (K <= 4) { FGVC_SIMT(4); }
+  if (K <= 10) { FGVC_SIMT(10); }
+  FGVC_SIMT(16);
+#undef FGVC_SIMT
 }
 
 }  // namespace fgvc

@@ -19,13 +19,33 @@ def pad4(n):
     return (n + 3) // 4 * 4
 
 
-class FeatureBank:
-    """feat[slot][2][H*W][C]: L2-normalised, pixel-major, TF32 hi/lo split (K0 output)."""
+def default_split(C):
+    """'f16' (three-term fp16 split, all-TMEM operands: the fast tensor engine) when the channel
+    count allows, else 'tf32' (3xTF32)."""
+    return "f16" if (C % 64 == 0 and C <= 256) else "tf32"
 
-    def __init__(self, n_slots, C, H, W, device):
+
+class FeatureBank:
+    """feat[slot][2][H*W][C]: L2-normalised, pixel-major two-term split (K0 output).
+    ``split='tf32'``: fp32 cells, hi = tf32(x), lo = x - hi (3xTF32 engine);
+    ``split='f16'``: fp16 cells, hi = fp16(x), lo = fp16((x - hi) * 2^11) (fp16 three-term engine)."""
+
+    def __init__(self, n_slots, C, H, W, device, split=None):
         _lib.require_cuda()
         self.n_slots, self.C, self.H, self.W = n_slots, C, H, W
-        self.buf = torch.empty(n_slots, 2, H * W, C, dtype=torch.float32, device=device)
+        self.split = split or default_split(C)
+        assert self.split in ("tf32", "f16")
+        if self.split == "f16" and C % 4:
+            raise ValueError("the f16 bank needs C % 4 == 0")
+        self.fmt = _lib.BANK_F16 if self.split == "f16" else _lib.BANK_TF32
+        dt = torch.float16 if self.split == "f16" else torch.float32
+        self.buf = torch.empty(n_slots, 2, H * W, C, dtype=dt, device=device)
+
+    def dense(self):
+        """fp32 [slot, H*W, C] view of what the split encodes (tests / diagnostics)."""
+        if self.split == "f16":
+            return self.buf[:, 0].float() + self.buf[:, 1].float() / 2048.0
+        return self.buf[:, 0] + self.buf[:, 1]
 
     def load(self, src, first_slot, n_frames, frame_stride, chan_stride, normalize=True):
         """src: fp32 CUDA tensor; frame f / channel c / pixel p at
@@ -33,7 +53,7 @@ class FeatureBank:
         assert src.is_cuda and src.dtype == torch.float32
         assert 0 <= first_slot and first_slot + n_frames <= self.n_slots
         call("fgvc_prep_features", ptr(src), frame_stride, chan_stride, n_frames, self.C, self.H, self.W,
-             int(bool(normalize)), ptr(self.buf), first_slot, stream_ptr())
+             int(bool(normalize)), ptr(self.buf), self.fmt, first_slot, stream_ptr())
 
     def load_frames(self, feats, first_slot=0, normalize=True):
         """feats [n,C,H,W] contiguous."""
@@ -139,7 +159,7 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
-    call("fgvc_affinity_topk", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C,
+    call("fgvc_affinity_topk", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
          ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
          ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),
          int(engine), stream_ptr())
@@ -202,7 +222,8 @@ def c2f_propagate(coarse, fine, table, job_index, fine_labels, radius, radius_fi
     si = torch.empty(n_mem * nq, dtype=torch.int32, device=dev)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     jptr = ctypes.c_void_p(jobs.data_ptr() + 16 * job_index)
-    call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.n_slots, coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
+    assert coarse.fmt == fine.fmt
+    call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.fmt, coarse.n_slots, coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
          jptr, ctypes.byref(hj), ptr(mem_feat), ptr(mem_label), int(radius), mode, int(radius_fine), int(K),
          float(temperature), ptr(fine_labels.buf), fine_labels.Lp, ptr(out), ptr(sv), ptr(si), int(engine),
          stream_ptr())
@@ -215,11 +236,11 @@ class MaskClipPropagator:
     over all frames' jobs, then per frame K1b gather -> NCHW -> decode (bilinear up-sample,
     min-max normalise, argmax).  ``events=True`` records CUDA events around K1."""
 
-    def __init__(self, T, C, H, W, L, out_hw, cfg, device, engine_id=_lib.ENGINE_AUTO):
+    def __init__(self, T, C, H, W, L, out_hw, cfg, device, engine_id=_lib.ENGINE_AUTO, split=None):
         self.T, self.C, self.H, self.W, self.L, self.out_hw, self.cfg = T, C, H, W, L, tuple(out_hw), cfg
         self.engine_id = engine_id
         self.device = device
-        self.bank = FeatureBank(T, C, H, W, device)
+        self.bank = FeatureBank(T, C, H, W, device, split=split or cfg.get("split"))
         self.labels = LabelBank(T, L, H, W, device)
         self.table = JobTable()
         nr = cfg.get("neighbor_range", None)

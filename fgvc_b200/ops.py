@@ -112,7 +112,7 @@ def _check_common(query, key, value, mode, sim_mode, topk):
 
 
 def _propagate(query, key, value, radius, mask_mode, temperature, topk, normalize, non_mask_len, engine_id,
-               groups=None):
+               groups=None, split=None):
     C, Hq, Wq = query.shape[1:]
     T, Hk, Wk = key.shape[2:]
     L = value.size(1)
@@ -122,7 +122,9 @@ def _propagate(query, key, value, radius, mask_mode, temperature, topk, normaliz
     query = query.float().contiguous()
     key = key.float().contiguous()
     value = value.float().contiguous()
-    feats = FeatureBank(T + 1, C, Hk, Wk, dev)
+    if split is None and C % 4 == 0 and engine_id == _lib.ENGINE_SIMT:
+        split = "tf32"          # the CUDA-core engine then sees the exact fp32 values
+    feats = FeatureBank(T + 1, C, Hk, Wk, dev, split=split)
     feats.load(key, 0, T, Hk * Wk, T * Hk * Wk, normalize)          # key[0,:,t] in place
     feats.load(query, T, 1, 0, Hq * Wq, normalize)
     labels = LabelBank(T + 1, L, Hk, Wk, dev)
@@ -137,7 +139,8 @@ def _propagate(query, key, value, radius, mask_mode, temperature, topk, normaliz
 
 
 def masked_attention_efficient(query, key, value, mask, temperature=1, topk=None, normalize=True, step=32,
-                               non_mask_len=0, mode="softmax", sim_mode="dot_product", engine_id=_lib.ENGINE_AUTO):
+                               non_mask_len=0, mode="softmax", sim_mode="dot_product", engine_id=_lib.ENGINE_AUTO,
+                               split=None):
     """query [1,C,H,W]; key [1,C,T,H,W]; value [1,L,T,H,W]; mask bool [H*W,H*W] or None.
     Returns [1,L,H,W] on the input device (local_attention.py:267-389)."""
     _check_common(query, key, value, mode, sim_mode, topk)
@@ -152,12 +155,13 @@ def masked_attention_efficient(query, key, value, mask, temperature=1, topk=None
         radius, mask_mode = None, "circle"
     else:
         mask_mode, radius = _mask_spec(mask, key.shape[3], key.shape[4], query.shape[2], query.shape[3])
-    return _propagate(query, key, value, radius, mask_mode, temperature, topk, normalize, non_mask_len, engine_id)
+    return _propagate(query, key, value, radius, mask_mode, temperature, topk, normalize, non_mask_len, engine_id,
+                      split=split)
 
 
 def masked_attention_efficient_v2(query, key, value, radius, temperature=1, topk=None, normalize=True, step=32,
                                   non_mask_len=0, mode="softmax", sim_mode="dot_product",
-                                  engine_id=_lib.ENGINE_AUTO):
+                                  engine_id=_lib.ENGINE_AUTO, split=None):
     """Radius given directly; every memory frame is masked (local_attention.py:392-508,
     which accepts but never reads non_mask_len / sim_mode)."""
     _check_common(query, key, value, mode, "dot_product", topk)
@@ -167,12 +171,13 @@ def masked_attention_efficient_v2(query, key, value, radius, temperature=1, topk
         value = value.unsqueeze(2)
     assert value.ndim == key.ndim == 5
     assert 0 <= non_mask_len < key.size(2)
-    return _propagate(query, key, value, int(radius), "circle", temperature, topk, normalize, 0, engine_id)
+    return _propagate(query, key, value, int(radius), "circle", temperature, topk, normalize, 0, engine_id,
+                      split=split)
 
 
 def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask, temperature=1, topk=None,
                                    normalize=True, step=32, non_mask_len=0, mode="softmax",
-                                   sim_mode="dot_product", radius_fine=12, engine_id=_lib.ENGINE_AUTO):
+                                   sim_mode="dot_product", radius_fine=12, engine_id=_lib.ENGINE_AUTO, split=None):
     """Coarse-to-fine propagation (local_attention.py:721-880).  ``value`` lives on the FINE
     grid [1,L,T,s*Hk,s*Wk]; the output on the COARSE query grid [1,L,Hq,Wq]."""
     _check_common(query, key, value, mode, sim_mode, topk)
@@ -194,11 +199,13 @@ def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask
         mask_mode, radius = _mask_spec(mask, Hk, Wk, Hq, Wq)
         unmasked = non_mask_len
     dev = query.device
-    coarse = FeatureBank(T + 1, C, Hk, Wk, dev)
+    if split is None:
+        split = "f16" if (engine.default_split(C) == "f16" and Cf % 4 == 0 and engine_id != _lib.ENGINE_SIMT) else "tf32"
+    coarse = FeatureBank(T + 1, C, Hk, Wk, dev, split=split)
     key = key.float().contiguous()
     coarse.load(key, 0, T, Hk * Wk, T * Hk * Wk, normalize)
     coarse.load(query.float().contiguous(), T, 1, 0, Hq * Wq, normalize)
-    fine = FeatureBank(T + 1, Cf, Hf, Wf, dev)
+    fine = FeatureBank(T + 1, Cf, Hf, Wf, dev, split=split)
     key_fine = key_fine.float().contiguous()
     fine.load(key_fine, 0, T, Hf * Wf, T * Hf * Wf, normalize)
     fine.load(query_fine.float().contiguous(), T, 1, 0, Hf * Wf, normalize)

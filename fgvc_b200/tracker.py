@@ -96,7 +96,7 @@ class VanillaTracker(nn.Module):
         if cfg.get("sim_mode", "dot_product") != "dot_product":
             raise NotImplementedError("sim_mode='l2-distance' is not built")
 
-        bank = FeatureBank(T, C, Hf, Wf, dev)
+        bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
         bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
 
         table = JobTable()

@@ -15,9 +15,9 @@
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  *
  * Data layout in HBM (all fp32 unless noted)
- *   feature bank  feat[slot][2][H*W][C]   part 0 = TF32-rounded "hi", part 1 = x - hi
- *                 ("lo"); rows are L2-normalised over C; pixel-major so that the channel
- *                 (contraction) dimension is contiguous = K-major MMA operands.
+ *   feature bank  feat[slot][2][H*W][C]   part 0 = "hi", part 1 = "lo" of a two-term split of
+ *                 the L2-normalised row (fgvc_bank_format: fp32/TF32 or fp16); pixel-major so
+ *                 that the channel (contraction) dimension is contiguous = K-major MMA operands.
  *   label bank    lab[slot][H*W][Lp]      Lp = L rounded up to a multiple of 4 (float4
  *                 rows); pixel-major so that the k winners of a query are k coalesced rows.
  *   top-k lists   val[job][group][Nq][K], idx[job][group][Nq][K] (int32,
@@ -56,10 +56,18 @@ typedef enum fgvc_status {
   FGVC_ERR_UNSUPPORTED = -3  /* valid in the reference but not built here */
 } fgvc_status;
 
+/* feature-bank formats (both hold an L2-normalised frame as a two-term split, pixel-major):
+ *   TF32: fp32 [slot][2][H*W][C], hi = tf32(x), lo = x - hi            -> 3xTF32 tensor engine
+ *   F16 : fp16 [slot][2][H*W][C], hi = fp16(x), lo = fp16((x - hi) * 2^11) -> 3-term fp16 tensor
+ *         engine (same 11 + 11 significant bits per operand, twice the MMA depth per instruction,
+ *         half the bytes).  Needs C % 64 == 0. */
+typedef enum fgvc_bank_format { FGVC_BANK_TF32 = 0, FGVC_BANK_F16 = 1 } fgvc_bank_format;
+
 typedef enum fgvc_mask_mode { FGVC_MASK_CIRCLE = 0, FGVC_MASK_SQUARE = 1 } fgvc_mask_mode;
 
-/* affinity engines of K1.  AUTO picks the tcgen05 kernel whenever the shape allows
- * (C % 32 == 0, K <= 16); SIMT is the exact-fp32 CUDA-core kernel for every other shape. */
+/* affinity engines of K1.  AUTO picks the tcgen05 kernel matching the bank format whenever the
+ * shape allows (TF32 bank: C % 32 == 0; F16 bank: C % 64 == 0; K <= 16); SIMT is the fp32
+ * CUDA-core kernel for every other shape. */
 typedef enum fgvc_engine { FGVC_ENGINE_AUTO = 0, FGVC_ENGINE_SIMT = 1, FGVC_ENGINE_TCGEN05 = 2 } fgvc_engine;
 
 /* One propagation job = one query frame and its memory list (a multiset of frames:
@@ -88,7 +96,7 @@ FGVC_API int64_t fgvc_launch_count(void);
  * first_slot .. first_slot+n_frames-1. */
 FGVC_API int fgvc_prep_features(const float* src, int64_t src_frame_stride, int64_t src_chan_stride,
                        int32_t n_frames, int32_t C, int32_t H, int32_t W, int32_t normalize,
-                       float* feat_bank, int32_t first_slot, void* stream);
+                       void* feat_bank, int32_t bank_format, int32_t first_slot, void* stream);
 
 /* label layout conversions: NCHW [L][H*W] (channel stride src_chan_stride) <-> pixel-major */
 FGVC_API int fgvc_labels_to_pixmajor(const float* src, int64_t src_chan_stride, int32_t L, int32_t n_pix,
@@ -103,7 +111,7 @@ FGVC_API int fgvc_gaussian_labels(const float* points_xy, int32_t P, int32_t H, 
                          float sigma, float* lab_bank, int32_t slot, int32_t Lp, void* stream);
 
 /* 1 when the tcgen05 engine of K1 takes this shape, else 0 (AUTO then uses the SIMT engine) */
-FGVC_API int fgvc_tc_supported(int32_t H, int32_t W, int32_t C, int32_t K);
+FGVC_API int fgvc_tc_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K);
 
 /* workspace bytes for the top-k lists of n_jobs jobs */
 FGVC_API int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K);
@@ -112,7 +120,7 @@ FGVC_API int64_t fgvc_topk_bytes(int32_t n_jobs, int32_t groups, int32_t n_query
  * (local_attention.py:318-356 without materialising the affinity).  The memory list of
  * each job is split into `groups` contiguous parts (load balance for short job lists);
  * fgvc_gather_labels merges them.  K in [1,16]; radius = neighbor_range // 2. */
-FGVC_API int fgvc_affinity_topk(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                        const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
@@ -120,7 +128,7 @@ FGVC_API int fgvc_affinity_topk(const float* feat_bank, int32_t n_slots, int32_t
 /* test hook (tcgen05 engine, groups = 1, use with ONE query tile): additionally dumps the
  * raw 128 x 128 accumulator tile of the first dbg_max_boxes key boxes to
  * dbg[box][query_row][key_col] and (mem entry, box y, box x, N) to dbg_meta[box][4]. */
-FGVC_API int fgvc_debug_affinity_boxes(const float* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+FGVC_API int fgvc_debug_affinity_boxes(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                        const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                        int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,
                        int32_t* topk_idx, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes,
@@ -181,8 +189,8 @@ FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx
  * T*R^2, softmax, gather of FINE labels.  Output on the coarse grid: out[Hc*Wc][Lp].
  * job_dev / job_host: the same job in device memory (read by K1) and host memory (read by
  * the launcher); scratch_val / scratch_idx: n_mem * Hc*Wc elements each. */
-FGVC_API int fgvc_c2f_propagate(const float* coarse_bank, int32_t n_slots, int32_t Hc, int32_t Wc, int32_t C,
-                       const float* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
+FGVC_API int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, int32_t n_slots, int32_t Hc, int32_t Wc,
+                       int32_t C, const void* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
                        const fgvc_job* job_dev, const fgvc_job* job_host,
                        const int32_t* mem_feat_slot, const int32_t* mem_label_slot, int32_t radius,
                        int32_t mask_mode, int32_t radius_fine, int32_t K, float temperature,

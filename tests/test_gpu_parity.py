@@ -21,18 +21,24 @@ TIGHT = 2e-5        # what we actually expect away from ties
 GAP_EPS = 3e-5      # affinity/temperature units: cos gap 2e-6 at temperature 0.07
 
 
-ENGINES = ["simt", "tc"]
+# engine name -> (engine id, feature-bank split): CUDA-core fp32, tcgen05 3xTF32, tcgen05 fp16 three-term
+ENGINES = ["simt", "tc", "tc16"]
 
 
-def _eid(name):
+def _eng(name):
     import fgvc_b200
-    return {"simt": fgvc_b200.ENGINE_SIMT, "tc": fgvc_b200.ENGINE_TCGEN05, "auto": fgvc_b200.ENGINE_AUTO}[name]
+    return {"simt": dict(engine_id=fgvc_b200.ENGINE_SIMT, split="tf32"),
+            "simt16": dict(engine_id=fgvc_b200.ENGINE_SIMT, split="f16"),
+            "tc": dict(engine_id=fgvc_b200.ENGINE_TCGEN05, split="tf32"),
+            "tc16": dict(engine_id=fgvc_b200.ENGINE_TCGEN05, split="f16"),
+            "auto": dict(engine_id=fgvc_b200.ENGINE_AUTO)}[name]
 
 
 def _skip_if_tc_unsupported(name, C, H=64, W=64, K=10):
     from fgvc_b200 import _lib
-    if name == "tc" and not _lib.load().fgvc_tc_supported(H, W, C, K):
-        pytest.skip("tcgen05 engine does not take this shape (needs C % 32 == 0)")
+    fmt = {"tc": _lib.BANK_TF32, "tc16": _lib.BANK_F16}.get(name)
+    if fmt is not None and not _lib.load().fgvc_tc_supported(fmt, H, W, C, K):
+        pytest.skip("tcgen05 engine does not take this shape (3xTF32: C % 32 == 0; fp16 split: C % 64 == 0, C <= 256)")
 
 
 def _coherent(g, T, C, H, W):
@@ -74,7 +80,7 @@ def test_operators_match_reference_golden(golden_dir, name, engine):
     T = k.shape[2]
     mask = fgvc_b200.spatial_neighbor(1, H, W, nr, q.device, torch.float32)
     got = fgvc_b200.masked_attention_efficient(q, k, v, mask, temperature=0.07, topk=topk, step=64,
-                                               non_mask_len=nml, engine_id=_eid(engine))
+                                               non_mask_len=nml, **_eng(engine))
     assert got.shape == d["out_v1"].shape and got.is_cuda
     ex = O.propagate_exact(q.cpu(), k.cpu(), v.cpu(), radius=nr // 2, temperature=0.07, topk=topk,
                            masked=[t >= nml for t in range(T)])
@@ -83,7 +89,7 @@ def test_operators_match_reference_golden(golden_dir, name, engine):
     assert float((err * clear).max()) < TIGHT
     assert float((err.amax(1, keepdim=True) > TOL).float().mean()) <= 1e-3 + 2.0 / (H * W)
     got2 = fgvc_b200.masked_attention_efficient_v2(q, k, v, nr // 2, temperature=0.07, topk=topk,
-                                                   engine_id=_eid(engine))
+                                                   **_eng(engine))
     err2 = (got2.cpu() - torch.from_numpy(d["out_v2"])).abs()
     ex2 = O.propagate_exact(q.cpu(), k.cpu(), v.cpu(), radius=nr // 2, temperature=0.07, topk=topk)
     clear2 = ((ex2["gap"] > GAP_EPS) | (ex2["gap"] == 0)).view(1, 1, H, W)
@@ -132,7 +138,7 @@ def test_propagate_matches_oracle(ci, engine):
     nr = 2 * r + (1 if mode == "circle" else 0)       # radius = nr // 2 either way
     mask = fgvc_b200.spatial_neighbor(1, H, W, nr, "cuda", torch.float32, mode=mode)
     got = fgvc_b200.masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), mask, temperature=0.07, topk=topk,
-                                               non_mask_len=nml, engine_id=_eid(engine))
+                                               non_mask_len=nml, **_eng(engine))
     rep = _report(got, q, k, v, r, topk, masked=[t >= nml for t in range(T)], mask_mode=mode)
     _assert_parity(rep)
 
@@ -150,7 +156,7 @@ def test_config1_geometry_vs_port(engine):
     lab = torch.rand(6, L, H, W, generator=g)
     v = lab[mem].permute(1, 0, 2, 3)[None].contiguous()
     got = fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 12, temperature=0.07, topk=10,
-                                                  engine_id=_eid(engine))
+                                                  **_eng(engine))
     rep = _report(got, q, k, v, 12, 10)
     _assert_parity(rep)
     port = O.propagate_port(q, k, v, radius=12, temperature=0.07, topk=10, step=512)
@@ -165,10 +171,12 @@ def test_groups_do_not_change_results():
     f = _coherent(g, 6, 64, 24, 28).cuda()
     q, k = f[5][None], f[:5].permute(1, 0, 2, 3)[None].contiguous()
     v = torch.rand(1, 5, 5, 24, 28, generator=g).cuda()
-    base = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, _eid("simt"), groups=1)
-    for gr in (2, 3, 5):
-        out = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, _eid("simt"), groups=gr)
-        assert torch.equal(out, base)
+    import fgvc_b200
+    for eng, split in ((fgvc_b200.ENGINE_SIMT, "tf32"), (fgvc_b200.ENGINE_TCGEN05, "f16")):
+        base = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, eng, groups=1, split=split)
+        for gr in (2, 3, 5):
+            out = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, eng, groups=gr, split=split)
+            assert torch.equal(out, base)
 
 
 def test_engines_agree_on_clear_queries():
@@ -178,13 +186,12 @@ def test_engines_agree_on_clear_queries():
     f = _coherent(g, 4, 128, 30, 40)
     q, k = f[3][None], f[:3].permute(1, 0, 2, 3)[None].contiguous()
     v = torch.rand(1, 6, 3, 30, 40, generator=g)
-    a = fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 6, temperature=0.07, topk=10,
-                                                engine_id=_eid("simt"))
-    b = fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 6, temperature=0.07, topk=10,
-                                                engine_id=_eid("tc"))
     ex = O.propagate_exact(q, k, v, radius=6, temperature=0.07, topk=10)
     clear = (ex["gap"] > GAP_EPS).view(1, 1, 30, 40).cuda()
-    assert float(((a - b).abs() * clear).max()) < TIGHT
+    outs = [fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 6, temperature=0.07, topk=10,
+                                                    **_eng(name)) for name in ("simt", "simt16", "tc", "tc16")]
+    for o in outs[1:]:
+        assert float(((outs[0] - o).abs() * clear).max()) < TIGHT
 
 
 # ---------------------------------------------------------- size-independent properties
@@ -200,21 +207,21 @@ def test_properties_at_full_size(engine):
     k = f[[0, 0, 1, 2] * 5 + [1]].permute(1, 0, 2, 3)[None].contiguous()
     q = f[3][None]
     ones = torch.ones(1, L, T, H, W, device="cuda")
-    out = fgvc_b200.masked_attention_efficient_v2(q, k, ones, 12, temperature=0.07, topk=10, engine_id=_eid(engine))
+    out = fgvc_b200.masked_attention_efficient_v2(q, k, ones, 12, temperature=0.07, topk=10, **_eng(engine))
     assert (out - 1).abs().max() < 1e-5
     v1 = torch.rand(1, L, T, H, W, generator=g).cuda()
     v2 = torch.rand(1, L, T, H, W, generator=g).cuda()
-    o1 = fgvc_b200.masked_attention_efficient_v2(q, k, v1, 12, temperature=0.07, topk=10, engine_id=_eid(engine))
-    o2 = fgvc_b200.masked_attention_efficient_v2(q, k, v2, 12, temperature=0.07, topk=10, engine_id=_eid(engine))
+    o1 = fgvc_b200.masked_attention_efficient_v2(q, k, v1, 12, temperature=0.07, topk=10, **_eng(engine))
+    o2 = fgvc_b200.masked_attention_efficient_v2(q, k, v2, 12, temperature=0.07, topk=10, **_eng(engine))
     o12 = fgvc_b200.masked_attention_efficient_v2(q, k, 2 * v1 - v2, 12, temperature=0.07, topk=10,
-                                                  engine_id=_eid(engine))
+                                                  **_eng(engine))
     assert (o12 - (2 * o1 - o2)).abs().max() < 1e-5
     assert float(o1.min()) >= 0 and float(o1.max()) <= 1 + 1e-6
     # a frame propagated from itself with k=1 copies its labels (cos = 1 on the diagonal)
     fr = torch.randn(1, C, H, W, generator=g).cuda()
     lab = torch.rand(1, L, 1, H, W, generator=g).cuda()
     same = fgvc_b200.masked_attention_efficient_v2(fr, fr[:, :, None], lab, 12, temperature=0.07, topk=1,
-                                                   engine_id=_eid(engine))
+                                                   **_eng(engine))
     assert torch.equal(same, lab[:, :, 0])
 
 
@@ -224,9 +231,13 @@ def test_prep_features_matches_normalize():
     g = torch.Generator().manual_seed(6)
     x = torch.randn(3, 96, 7, 9, generator=g).cuda()
     x[1, :, 2, 3] = 0                                   # zero vector: eps clamp, stays zero
-    bank = FeatureBank(4, 96, 7, 9, "cuda")
+    bank = FeatureBank(4, 96, 7, 9, "cuda", split="tf32")
     bank.load_frames(x, 1)
     want = torch.nn.functional.normalize(x, p=2, dim=1).permute(0, 2, 3, 1).reshape(3, 63, 96)
+    bank16 = FeatureBank(4, 96, 7, 9, "cuda", split="f16")
+    bank16.load_frames(x, 1)
+    assert bank16.buf.dtype == torch.float16
+    assert (bank16.dense()[1:] - want).abs().max() < 2e-7           # 11 + 11 significant bits, like 3xTF32
     hi, lo = bank.buf[1:, 0], bank.buf[1:, 1]
     assert (hi + lo - want).abs().max() < 2e-7
     assert (hi.view(torch.int32) & 0x1FFF).abs().max() == 0          # hi is a TF32 number
@@ -288,7 +299,7 @@ def test_c2f_matches_reference_golden(golden_dir, engine):
     mask = fgvc_b200.spatial_neighbor(1, H, W, int(d["neighbor_range"]), "cuda", torch.float32)
     got = fgvc_b200.masked_attention_efficient_c2f(t["q"], t["k"], t["qf"], t["kf"], t["v"], mask, temperature=0.07,
                                                    topk=int(d["topk"]), radius_fine=int(d["radius_fine"]),
-                                                   engine_id=_eid(engine))
+                                                   **_eng(engine))
     assert got.shape == d["out"].shape
     err = (got.cpu() - torch.from_numpy(d["out"])).abs().amax(dim=1).flatten()
     assert float((err > TOL).float().mean()) <= 0.05        # 42 queries: allow the odd tie
@@ -416,19 +427,19 @@ def test_raw_c_abi_as_in_integration_md():
     g = torch.Generator().manual_seed(12)
     feats = _coherent(g, T + 1, C, H, W).cuda()
     v = torch.rand(1, L, T, H, W, generator=g).cuda()
-    bank = torch.empty(T + 1, 2, H * W, C, device="cuda")
+    bank = torch.empty(T + 1, 2, H * W, C, device="cuda", dtype=torch.float16)       # FGVC_BANK_F16 = 1
     labels = torch.zeros(T + 1, H * W, 8, device="cuda")
     labels[:T] = v[0].permute(1, 2, 3, 0).reshape(T, H * W, L)
     st = P(torch.cuda.current_stream().cuda_stream)
     rc = lib.fgvc_prep_features(P(feats.data_ptr()), ctypes.c_int64(C * H * W), ctypes.c_int64(H * W), T + 1, C, H, W,
-                                1, P(bank.data_ptr()), 0, st)
+                                1, P(bank.data_ptr()), 1, 0, st)
     assert rc == 0, lib.fgvc_last_error()
     jobs = torch.tensor([[T, 0, T, T]], dtype=torch.int32, device="cuda")
     mem_feat = torch.arange(T, dtype=torch.int32, device="cuda")
     mem_lab = torch.arange(T, dtype=torch.int32, device="cuda")
     val = torch.empty(1, 1, H * W, K, device="cuda")
     idx = torch.empty(1, 1, H * W, K, dtype=torch.int32, device="cuda")
-    rc = lib.fgvc_affinity_topk(P(bank.data_ptr()), T + 1, H, W, C, P(jobs.data_ptr()), 1, P(mem_feat.data_ptr()),
+    rc = lib.fgvc_affinity_topk(P(bank.data_ptr()), 1, T + 1, H, W, C, P(jobs.data_ptr()), 1, P(mem_feat.data_ptr()),
                                 5, 0, K, 1, P(val.data_ptr()), P(idx.data_ptr()), 0, st)
     assert rc == 0, lib.fgvc_last_error()
     rc = lib.fgvc_gather_labels(P(val.data_ptr()), P(idx.data_ptr()), K, 1, P(jobs.data_ptr()), 0, 1,

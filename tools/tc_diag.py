@@ -15,6 +15,7 @@ from fgvc_b200._lib import call, ptr, stream_ptr  # noqa: E402
 CASES = {
     # name: (H, W, C, T, radius, topk)
     "one_box_c32": (8, 16, 32, 1, 40, 10),
+    "one_box_c128": (8, 16, 128, 1, 40, 10),
     "one_box_c64": (8, 16, 64, 1, 40, 10),
     "one_box_c256": (8, 16, 256, 1, 40, 10),
     "halo_c64": (24, 48, 64, 2, 5, 10),
@@ -23,12 +24,12 @@ CASES = {
 }
 
 
-def main(name):
+def main(name, split="tf32"):
     H, W, C, T, radius, K = CASES[name]
     torch.manual_seed(0)
     dev = "cuda"
     feats = torch.randn(T + 1, C, H, W, device=dev)
-    bank = engine.FeatureBank(T + 1, C, H, W, dev)
+    bank = engine.FeatureBank(T + 1, C, H, W, dev, split=split)
     bank.load_frames(feats)
     table = engine.JobTable()
     table.add(T, list(range(T)), list(range(T)), T)
@@ -39,16 +40,16 @@ def main(name):
     ti = torch.full((1, 1, nq, K), -7, dtype=torch.int32, device=dev)
     dbg = torch.full((maxb, 128, 128), float("nan"), device=dev)
     meta = torch.full((maxb, 4), -1, dtype=torch.int32, device=dev)
-    call("fgvc_debug_affinity_boxes", ptr(bank.buf), bank.n_slots, H, W, C, ptr(jobs), 1, ptr(mem_feat), radius, 0, K,
+    call("fgvc_debug_affinity_boxes", ptr(bank.buf), bank.fmt, bank.n_slots, H, W, C, ptr(jobs), 1, ptr(mem_feat), radius, 0, K,
          ptr(tv), ptr(ti), ptr(dbg), ptr(meta), maxb, stream_ptr())
     torch.cuda.synchronize()
-    x = (bank.buf[:, 0] + bank.buf[:, 1]).double()          # [slot, pix, C]
+    x = bank.dense().double()          # [slot, pix, C]
     meta = meta.cpu()
     # NOTE: with several query tiles every CTA dumps into the same buffer; the LAST writer
     # wins per box index, so only single-tile cases are exact here.  Use tile (0,0)'s view:
     reach = radius - 1
     qh, qw = (8, 16)
-    print(f"case {name}: H={H} W={W} C={C} T={T} r={radius}")
+    print(f"case {name} [{split}]: H={H} W={W} C={C} T={T} r={radius}")
     nb = int((meta[:, 0] >= 0).sum())
     print("boxes dumped:", nb, meta[:min(nb, 6)].tolist())
     if H <= 8 and W <= 16:
@@ -84,8 +85,9 @@ def main(name):
         print("worst:", worst)
     # end-to-end check of the lists against a dense fp64 computation
     from oracle import oracle as O
-    kk = feats[:T].permute(1, 0, 2, 3)[None].cpu()
-    ex = O.propagate_exact(feats[T][None].cpu(), kk, torch.zeros(1, 1, T, H, W), radius=radius, topk=K)
+    dn = bank.dense().view(T + 1, H, W, C).permute(0, 3, 1, 2).cpu()      # exactly what the kernel sees
+    kk = dn[:T].permute(1, 0, 2, 3)[None]
+    ex = O.propagate_exact(dn[T][None], kk, torch.zeros(1, 1, T, H, W), radius=radius, topk=K, normalize=False)
     got_idx = ti[0, 0].cpu().long()
     want_idx = ex["idx"]
     same = (got_idx.sort(1)[0] == want_idx.sort(1)[0]).all(1)
@@ -100,4 +102,4 @@ def main(name):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "tf32")

@@ -102,19 +102,32 @@ struct TopK {
       }
     }
   }
-  // caller guarantees x > thr()
+  // caller guarantees x > thr().  Select form of the sorted insert: K compares, then every slot
+  // takes its left neighbour, the new element or itself (equal values keep arrival order).
   __device__ __forceinline__ void push(float x, int i) {
-    v[K - 1] = x;
-    id[K - 1] = i;
+    bool c[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) c[j] = x > v[j];
 #pragma unroll
     for (int j = K - 1; j > 0; --j) {
-      if (v[j] > v[j - 1]) {
-        float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
-        int ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
-      }
+      v[j] = c[j - 1] ? v[j - 1] : (c[j] ? x : v[j]);
+      id[j] = c[j - 1] ? id[j - 1] : (c[j] ? i : id[j]);
     }
+    v[0] = c[0] ? x : v[0];
+    id[0] = c[0] ? i : id[0];
   }
 };
+
+// v[j] for a run-time j in [0,16): 4-level select tree (registers cannot be indexed dynamically)
+__device__ __forceinline__ float select16(const float* v, int j) {
+  float a[8], b[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+  const float c0 = (j & 4) ? b[1] : b[0], c1 = (j & 4) ? b[3] : b[2];
+  return (j & 8) ? c1 : c0;
+}
 
 // in-mask test shared by every kernel (affinity_utils.py:85-112):
 // circle: dy^2 + dx^2 < r^2 (strict); square: |dy| <= r and |dx| <= r

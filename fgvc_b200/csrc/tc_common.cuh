@@ -18,23 +18,36 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots burnt) until the
+// phase completes or the hint expires, instead of returning after the short default window
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The retry loop is
+// kept tiny (spinning warps share issue slots with the MMA / TMA warps of the same scheduler).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
+}
+// same for the epilogue warps, which wait about a box time (~1 us) per hand-off: sleep between
+// probes so that 16 waiting warps do not take issue slots from the warps that have work
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(256);
+    if (++spins > (1u << 24)) __trap();
+  } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3, int c4) {

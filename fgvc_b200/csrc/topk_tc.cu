@@ -263,16 +263,25 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       hi = min(hi - bx, 15);
       return hi >= lo ? (2u << hi) - (1u << lo) : 0u;
     };
-    auto scan16 = [&](const uint32_t* r, uint32_t bits, int kbase) {
+    auto scan16 = [&](const uint32_t* r, uint32_t bits, int kbase, bool active) {
+      // candidates = in-mask elements above the running K-th value; inserted in warp-wide rounds
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
       const float thr0 = top.thr();
-      float mx = -INFINITY;
+      uint32_t cand = 0;
+      if (active) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-      if (!(mx > thr0)) return;                       // nothing in this row can enter the list
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float v = __uint_as_float(r[j]);
-        if (v > top.thr() && ((bits >> j) & 1u)) top.push(v, kbase + j);
+        for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
+        cand &= bits;
+      }
+      while (__any_sync(0xffffffffu, cand != 0)) {
+        if (cand) {
+          const int j = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const float x = select16(v, j);
+          if (x > top.thr()) top.push(x, kbase + j);
+        }
       }
     };
     for (int e = e_hi - 1; e >= e_lo; --e) {   // newest memory frame first: thresholds rise early
@@ -309,8 +318,8 @@ affinity_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
             }
           }
-          if (doA && bitsA) scan16(ra, bitsA, pos_base + (by + rowA) * p.W + bx);
-          if (doB && bitsB) scan16(rb, bitsB, pos_base + (by + rowB) * p.W + bx);
+          if (doA) scan16(ra, bitsA, pos_base + (by + rowA) * p.W + bx, bitsA != 0);   // doA/doB are warp-uniform
+          if (doB) scan16(rb, bitsB, pos_base + (by + rowB) * p.W + bx, bitsB != 0);
           ++box_seq;
           tphase[buf] ^= 1;
           buf ^= 1;

@@ -16,7 +16,7 @@
 //     TS(A = lo_q, B = hi_k,                               N columns) -> D[N,2N) += lo_q*hi_k
 // The hi/lo key rows of a box are one TMA box (the "part" dimension of the 5-D map has
 // extent 2), landing stacked in one 128B-swizzled stage.  No query operand lives in shared
-// memory, so the ring is 12 stages deep (192 KB in flight).
+// memory, so the whole 192 KB ring streams key boxes (3 boxes of 64 KB in flight at C = 256).
 // TMEM: [0,128) accumulator 0, [128,256) accumulator 1, [256,384) hi_q, [384,512) lo_q.
 #include <stdlib.h>
 
@@ -30,7 +30,9 @@ constexpr int T16_MAX_BH = 4;                  // N <= 64, 2N <= 128 accumulator
 constexpr int T16_AHI_COL = 256, T16_ALO_COL = 384;
 constexpr int T16_EPI_WG = 4;
 constexpr int T16_THREADS = 64 + 128 * T16_EPI_WG;
-constexpr int T16_SMEM_BYTES = T16_STAGES * T16_STAGE_BYTES + 1024;
+constexpr int T16_MAX_BOXES = 1024;             // per box list (masked halo / whole frame)
+constexpr int T16_AUX_BYTES = 1024 + 2 * T16_MAX_BOXES * 4;
+constexpr int T16_SMEM_BYTES = T16_STAGES * T16_STAGE_BYTES + T16_AUX_BYTES;
 
 struct Tc16Params {
   int H, W, C, n_pix;
@@ -83,7 +85,12 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint64_t* a_bar = tempty_bar + 2;               // query operand written to TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
-  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);
+  int* nbox = reinterpret_cast<int*>(tmem_slot + 2);      // [2] number of boxes in each list
+  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);     // [reach+1] <= 128 entries
+  // box lists (by | bx << 16): [0] = radius halo of this query tile minus boxes no query can see,
+  // [1] = every box of the frame (unmasked memory entries).  Identical for all memory entries, so
+  // the three warp roles just walk a list instead of re-deriving the geometry per box.
+  uint32_t* boxes = reinterpret_cast<uint32_t*>(ring + T16_STAGES * T16_STAGE_BYTES + 1024);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,11 +103,15 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
   const int e_hi = min(job.mem_end, e_lo + per);
   const int N = 16 * p.BH;
   const int n_kc = p.C / 64;
-  const uint32_t stage_tx = (uint32_t)(2 * N * 128);
+  // one stage = one whole key box (all C channels: n_kc chunks of 16 KB), so the single issuing
+  // threads pay one barrier round trip per box instead of one per 64 channels
+  const int stage_bytes = n_kc * T16_STAGE_BYTES;
+  const int n_stages = (T16_STAGES * T16_STAGE_BYTES) / stage_bytes;
+  const uint32_t stage_tx = (uint32_t)(2 * N * 128 * n_kc);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
-    for (int s = 0; s < T16_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * T16_EPI_WG); }
     mbar_init(a_bar, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,6 +130,51 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     }
     halfw[d] = hw;
   }
+  if (warp == 2 || warp == 3) {          // one warp per list
+    const int li = warp - 2;
+    const Walk w = make_walk(p, li ? FGVC_MEM_UNMASKED : 0, qy0, qx0);
+    const int ncols = (w.x_hi - w.x_lo) / 16 + 1, nrows = (w.y_hi - w.y_lo) / p.BH + 1;
+    uint32_t* list = boxes + li * T16_MAX_BOXES;
+    int cnt = 0;
+    for (int base = 0; base < nrows * ncols; base += 32) {
+      const int i = base + lane;
+      const int by = w.y_lo + (i / ncols) * p.BH, bx = w.x_lo + (i % ncols) * 16;
+      const bool keep = i < nrows * ncols && !box_skipped(p, w, by, bx, qy0, qx0);
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+      if (keep && pos < T16_MAX_BOXES) list[pos] = (uint32_t)by | ((uint32_t)bx << 16);
+      cnt += __popc(bal);
+    }
+    cnt = min(cnt, T16_MAX_BOXES);
+    __syncwarp();
+    // Centre-out order for the halo list: the best matches of a query sit near its own position, so
+    // walking the boxes nearest to the tile first raises the running K-th values early and the
+    // (divergent, ~80-instruction) list insertions become rare.  Rank sort, n is a few dozen.
+    if (li == 0 && cnt > 1 && cnt <= 128) {
+      const int cy2 = 2 * qy0 + p.QH, cx2 = 2 * qx0 + p.QW;          // twice the tile centre
+      uint32_t mine[4]; int rank[4];
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * t;
+        mine[t] = i < cnt ? list[i] : 0u;
+        rank[t] = 0;
+      }
+      for (int j = 0; j < cnt; ++j) {
+        const uint32_t o = list[j];
+        const int oy = 2 * (int)(o & 0xffffu) + p.BH - cy2, ox = 2 * (int)(o >> 16) + 16 - cx2;
+        const int od = oy * oy + ox * ox;
+        for (int t = 0; t < 4; ++t) {
+          const int i = lane + 32 * t;
+          const int my = 2 * (int)(mine[t] & 0xffffu) + p.BH - cy2, mx = 2 * (int)(mine[t] >> 16) + 16 - cx2;
+          const int md = my * my + mx * mx;
+          rank[t] += (od < md || (od == md && j < i)) ? 1 : 0;
+        }
+      }
+      __syncwarp();
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < cnt) list[rank[t]] = mine[t];
+    }
+    if (lane == 0) nbox[li] = cnt;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,69 +182,68 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
 
   if (warp == 0) {
     // ================================ TMA producer ====================================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int e = e_hi - 1; e >= e_lo; --e) {
-      const int raw = p.mem_feat[e];
-      const int slot = raw & ~FGVC_MEM_UNMASKED;
-      const Walk w = make_walk(p, raw, qy0, qx0);
-      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
-        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
-          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
-          for (int kc = 0; kc < n_kc; ++kc) {
-            mbar_wait(empty_bar + stage, phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(full_bar + stage, stage_tx);
-              // one box = (64 channels, 16 x BH pixels, both parts): hi rows then lo rows
-              tma_load_5d(&tmap_k, full_bar + stage, ring + stage * T16_STAGE_BYTES, kc * 64, bx, by, 0, slot);
-            }
-            __syncwarp();
-            if (++stage == T16_STAGES) { stage = 0; phase ^= 1; }
-          }
+    // one elected lane runs the whole loop (the compiler then keeps everything in uniform registers)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int e = e_hi - 1; e >= e_lo; --e) {       // newest memory frame first: thresholds rise early
+        const int raw = p.mem_feat[e];
+        const int slot = raw & ~FGVC_MEM_UNMASKED;
+        const int li = (raw & FGVC_MEM_UNMASKED) ? 1 : 0;
+        const int nb = nbox[li];
+        for (int b = 0; b < nb; ++b) {
+          const uint32_t bb = boxes[li * T16_MAX_BOXES + b];
+          const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_expect_tx(full_bar + stage, stage_tx);
+          // per 64-channel chunk one TMA box = (64 channels, 16 x BH pixels, both parts): hi rows then lo rows
+          for (int kc = 0; kc < n_kc; ++kc)
+            tma_load_5d(&tmap_k, full_bar + stage, ring + stage * stage_bytes + kc * T16_STAGE_BYTES, kc * 64, bx, by,
+                        0, slot);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+      }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ================================= MMA issuer =====================================
-    const uint32_t idesc2 = make_idesc_f16(128, 2 * N), idesc1 = make_idesc_f16(128, N);
-    int stage = 0, buf = 0;
-    uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
     if (e_lo < e_hi) {
       mbar_wait(a_bar, 0);
       tc_fence_after();
     }
-    const uint32_t ring_u32 = smem_u32(ring);
-    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-    for (int e = e_hi - 1; e >= e_lo; --e) {
-      const int raw = p.mem_feat[e];
-      const Walk w = make_walk(p, raw, qy0, qx0);
-      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
-        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
-          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
-          mbar_wait(tempty_bar + buf, (buf ? tphase1 : tphase0) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-          for (int kc = 0; kc < n_kc; ++kc) {
-            mbar_wait(full_bar + stage, phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t b = desc_hi | (uint64_t)((ring_u32 + (uint32_t)(stage * T16_STAGE_BYTES)) >> 4);
-              const uint32_t a_hi = tmem_base + T16_AHI_COL + kc * 32, a_lo = tmem_base + T16_ALO_COL + kc * 32;
+    int n_total = 0;                                 // boxes this CTA processes
+    for (int e = e_lo; e < e_hi; ++e) n_total += nbox[(p.mem_feat[e] & FGVC_MEM_UNMASKED) ? 1 : 0];
+    if (elect_one()) {
+      const uint32_t idesc2 = make_idesc_f16(128, 2 * N), idesc1 = make_idesc_f16(128, N);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
+      const uint32_t ring_u32 = smem_u32(ring);
+      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+      for (int it = 0; it < n_total; ++it) {
+        mbar_wait(tempty_bar + buf, (buf ? tphase1 : tphase0) ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t sa = ring_u32 + (uint32_t)(stage * stage_bytes);
+        for (int kc = 0; kc < n_kc; ++kc) {
+          const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * T16_STAGE_BYTES)) >> 4);
+          const uint32_t a_hi = tmem_base + T16_AHI_COL + kc * 32, a_lo = tmem_base + T16_ALO_COL + kc * 32;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
-                const uint64_t o = (uint64_t)(ks * 2);
-                umma_f16_ts(d_tmem, a_hi + ks * 8, b + o, idesc2, (kc | ks) != 0);   // [hi*hi | hi*lo]
-                umma_f16_ts(d_tmem + N, a_lo + ks * 8, b + o, idesc1, 1);            // += lo*hi
-              }
-              umma_commit(empty_bar + stage);
-              if (kc == n_kc - 1) umma_commit(tfull_bar + buf);
-            }
-            __syncwarp();
-            if (++stage == T16_STAGES) { stage = 0; phase ^= 1; }
+          for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
+            const uint64_t o = (uint64_t)(ks * 2);
+            umma_f16_ts(d_tmem, a_hi + ks * 8, b + o, idesc2, (kc | ks) != 0);   // [hi*hi | hi*lo]
+            umma_f16_ts(d_tmem + N, a_lo + ks * 8, b + o, idesc1, 1);            // += lo*hi
           }
-          if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-          buf ^= 1;
         }
+        umma_commit(empty_bar + stage);     // smem stage free once these MMAs retire
+        umma_commit(tfull_bar + buf);       // accumulator complete
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+        buf ^= 1;
+      }
     }
+    __syncwarp();
   } else {
     // ================================== epilogue ======================================
     const int wg = (warp - 2) >> 2;
@@ -219,76 +274,86 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     TopK<K> top;
     top.init();
     int buf = 0;
-    uint32_t tphase[2] = {0, 0};
+    uint32_t tph0 = 0, tph1 = 0;
     int box_seq = 0;
-    for (int e = e_hi - 1; e >= e_lo; --e) {
+    const int row = wg;                                  // the key row of every box this warpgroup owns
+    const bool row_ok = qvalid && row < p.BH;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(row * 16);
+    for (int e = e_hi - 1; e >= e_lo; --e) {           // newest memory frame first: thresholds rise early
       const int raw = p.mem_feat[e];
-      const Walk w = make_walk(p, raw, qy0, qx0);
+      const bool masked = !(raw & FGVC_MEM_UNMASKED);
+      const int li = masked ? 0 : 1;
+      const int nb = nbox[li];
       const int pos_base = (e - job.mem_begin) * p.n_pix;
-      for (int by = w.y_lo; by <= w.y_hi; by += p.BH)
-        for (int bx = w.x_lo; bx <= w.x_hi; bx += 16) {
-          if (box_skipped(p, w, by, bx, qy0, qx0)) continue;
-          const int row = wg, ky = by + row;
-          // 16-bit interval mask of the in-mask, in-image keys of this key row
-          uint32_t bits = 0;
-          if (qvalid && row < p.BH && ky < p.H) {
-            int lo, hi;
-            if (w.masked) {
-              int ady = abs(ky - qy);
-              int hw = ady <= p.reach ? halfw[ady] : -1;
-              lo = hw < 0 ? 1 : max(qx - hw, 0);
-              hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
-            } else {
-              lo = 0; hi = p.W - 1;
-            }
-            lo = max(lo - bx, 0);
-            hi = min(hi - bx, 15);
-            if (hi >= lo) bits = (2u << hi) - (1u << lo);
+      for (int b = 0; b < nb; ++b) {
+        const uint32_t bb = boxes[li * T16_MAX_BOXES + b];
+        const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
+        const int ky = by + row;
+        // 16-bit interval mask of the in-mask, in-image keys of this key row
+        uint32_t bits = 0;
+        if (row_ok && ky < p.H) {
+          int lo = 0, hi = p.W - 1;
+          if (masked) {
+            const int ady = abs(ky - qy);
+            const int hw = ady <= p.reach ? halfw[ady] : -1;
+            lo = hw < 0 ? 1 : max(qx - hw, 0);
+            hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
           }
-          const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes && row < p.BH;
-          const bool doit = __any_sync(0xffffffffu, bits != 0) || dump;    // warp-uniform
-          mbar_wait(tfull_bar + buf, tphase[buf]);
-          tc_fence_after();
-          uint32_t r1[16], r2[16];
-          if (doit) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + row * 16);
-            tmem_ld16_issue(taddr, r1);
-            tmem_ld16_issue(taddr + (uint32_t)N, r2);
-            tmem_ld_wait(r1);
-            reg_fence16(r2);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + buf);
-          if (doit) {
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r2[j]), FGVC_F16_LO_INV, __uint_as_float(r1[j]));
-            if (dump) {
-              float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) d[j] = v[j];
-              if (p.dbg_meta != nullptr && m == 0 && wg == 0) {
-                p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
-                p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
-              }
-            }
-            if (bits) {
-              float mx = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
-              if (mx > top.thr()) {
-                const int kbase = pos_base + ky * p.W + bx;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (v[j] > top.thr() && ((bits >> j) & 1u)) top.push(v[j], kbase + j);
-              }
-            }
-          }
-          ++box_seq;
-          tphase[buf] ^= 1;
-          buf ^= 1;
+          lo = max(lo - bx, 0);
+          hi = min(hi - bx, 15);
+          if (hi >= lo) bits = (2u << hi) - (1u << lo);
         }
+        const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes && row < p.BH;
+        const bool doit = __any_sync(0xffffffffu, bits != 0) || dump;    // warp-uniform
+        mbar_wait_sleep(tfull_bar + buf, buf ? tph1 : tph0);
+        tc_fence_after();
+        uint32_t r1[16], r2[16];
+        if (doit) {
+          const uint32_t taddr = lane_base + (uint32_t)(buf * 128);
+          tmem_ld16_issue(taddr, r1);
+          tmem_ld16_issue(taddr + (uint32_t)N, r2);
+          tmem_ld_wait(r1);
+          reg_fence16(r2);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + buf);    // accumulator is in registers: hand the tile back
+        if (buf) tph1 ^= 1; else tph0 ^= 1;
+        buf ^= 1;
+        if (doit) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r2[j]), FGVC_F16_LO_INV, __uint_as_float(r1[j]));
+          if (dump) {
+            float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = v[j];
+            if (p.dbg_meta != nullptr && m == 0 && wg == 0) {
+              p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
+              p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
+            }
+          }
+          // candidates = in-mask elements above the running K-th value
+          const float thr0 = top.thr();
+          uint32_t cand = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
+          cand &= bits;
+          // Insert candidates in warp-wide rounds: in every round each lane that still has a
+          // candidate takes its next one, so a round serves ~4 lanes at once instead of one
+          // divergent insertion per (lane, element).
+          const int kbase = pos_base + ky * p.W + bx;
+          while (__any_sync(0xffffffffu, cand != 0)) {
+            if (cand) {
+              const int j = __ffs(cand) - 1;
+              cand &= cand - 1;
+              const float x = select16(v, j);
+              if (x > top.thr()) top.push(x, kbase + j);
+            }
+          }
+        }
+        ++box_seq;
+      }
     }
     // ---- merge the partial lists of the warpgroups through the (now idle) ring
     asm volatile("bar.sync 1, %0;" ::"n"(128 * T16_EPI_WG) : "memory");
@@ -349,7 +414,7 @@ bool tc16_supported(int H, int W, int C, int K) {
 }
 
 // all MMAs are TS-form: a box costs ~N plus a small fixed hand-shake
-static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 8); }
+static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 24); }
 static int pick_bh16(int rows) {
   int best = T16_MAX_BH;
   for (int bh = T16_MAX_BH - 1; bh >= 1; --bh)
@@ -386,6 +451,8 @@ int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C
   p.jobs = jobs; p.mem_feat = mem_feat; p.tv = tv; p.ti = ti;
   p.dbg = dbg; p.dbg_meta = dbg_meta; p.dbg_max_boxes = dbg_max_boxes;
   FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 f16 engine: radius %d too large", radius);
+  FGVC_CHECK_ARG(cdiv(H, p.BH) * cdiv(W, 16) <= T16_MAX_BOXES && H < 65536 && W < 65536,
+                 "tcgen05 f16 engine: %dx%d map has too many key boxes", H, W);
   CUtensorMap mk;
   int rc = make_map16(&mk, bank, n_slots, H, W, C, p.BH);
   if (rc) return rc;

@@ -17,20 +17,21 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
   FGVC_CHECK_ARG(L > 0 && L <= 255 && Lp >= L && Lp % 4 == 0, "fgvc_mask_clip_tail: bad label sizes");
   const int n_pix = H * W;
   const int64_t mask_elems = (int64_t)out_h * out_w;
+  (void)mask_elems;
+  // the recurrence lives only in the gather: run the chain first ...
   for (int j = job_begin; j < job_end; ++j) {
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
                                 temperature, lab_bank, Lp, stream);
     if (rc) return rc;
-    const int slot = jobs_host[j].out_slot;
     if (maps_nchw) {
+      const int slot = jobs_host[j].out_slot;
       rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
       if (rc) return rc;
     }
-    rc = launch_decode(lab_bank + (int64_t)slot * n_pix * Lp, true, L, Lp, H, W, out_h, out_w,
-                       reinterpret_cast<uint32_t*>(scratch_minmax), masks + slot * mask_elems, (cudaStream_t)stream);
-    if (rc) return rc;
   }
-  return FGVC_OK;
+  // ... then decode every frame of the range in two batched launches (scratch: [n_jobs][2L] words)
+  return launch_decode_jobs(lab_bank, jobs_dev, job_begin, job_end, L, Lp, H, W, out_h, out_w,
+                            reinterpret_cast<uint32_t*>(scratch_minmax), masks, (cudaStream_t)stream);
 }
 
 // Point tracking tail: gather + fused up-sample / soft-argmax per frame (K3 reads NCHW maps,

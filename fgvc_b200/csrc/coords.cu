@@ -224,6 +224,133 @@ decode_argmax_kernel(const float* __restrict__ src, int L, int H, int W, int str
   out[o] = (uint8_t)arg;
 }
 
+// batched form for a clip: blockIdx.y walks jobs [job_begin, job_end); each decodes the label-bank
+// slot jobs[j].out_slot into masks[slot] using minmax[j - job_begin][2L]
+// first / last output index whose source cell (floor of the clamped source coordinate) is i0
+__device__ __forceinline__ void cell_range(int i0, int in_size, int out_size, float scale, int* lo, int* hi) {
+  // lerp_coord(o).i0 is non-decreasing in o: locate the run of outputs that map to i0 by search
+  // around the analytic estimate (scale = in/out, src = (o + 0.5) * scale - 0.5)
+  int g = (int)floorf(((float)i0 + 0.5f) / scale - 0.5f);
+  g = max(0, min(out_size - 1, g));
+  while (g > 0 && lerp_coord(g - 1, scale, in_size).i0 >= i0) --g;
+  while (g < out_size - 1 && lerp_coord(g, scale, in_size).i0 < i0) ++g;
+  *lo = g;                       // first o with i0(o) >= i0
+  int h = g;
+  while (h < out_size - 1 && lerp_coord(h + 1, scale, in_size).i0 <= i0) ++h;
+  *hi = h;
+}
+
+// Per-channel min / max of the up-sampled map.  Within one source cell the bilinear value is
+// monotone along each axis, so its extremes over the output pixels of that cell sit on the four
+// corner-most output pixels: 4 evaluations per cell instead of (out/in)^2.  One thread per source
+// cell; the values are produced by the same tap arithmetic as the arg-max pass.
+__global__ void __launch_bounds__(256)
+decode_minmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int L,
+                          int Lp, int H, int W, int out_h, int out_w, uint32_t* __restrict__ minmax) {
+  extern __shared__ uint32_t skey[];   // [2L]
+  const int slot = jobs[job_begin + blockIdx.y].out_slot;
+  const float* src = lab + (int64_t)slot * H * W * Lp;
+  uint32_t* mm = minmax + (int64_t)blockIdx.y * 2 * L;
+  for (int i = threadIdx.x; i < 2 * L; i += 256) skey[i] = i < L ? 0xffffffffu : 0u;
+  __syncthreads();
+  const int cell = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = cell < H * W;
+  const float sy = (float)H / (float)out_h, sx = (float)W / (float)out_w;
+  int oy[2] = {0, 0}, ox[2] = {0, 0};
+  bool any = false;
+  if (valid) {
+    cell_range(cell / W, H, out_h, sy, &oy[0], &oy[1]);
+    cell_range(cell % W, W, out_w, sx, &ox[0], &ox[1]);
+    any = lerp_coord(oy[0], sy, H).i0 == cell / W && lerp_coord(ox[0], sx, W).i0 == cell % W;   // cell has outputs
+  }
+  Tap t[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) t[c] = make_tap(oy[c >> 1], ox[c & 1], H, W, sy, sx);
+  for (int l = 0; l < L; ++l) {
+    float mn = INFINITY, mx = -INFINITY;
+    if (any) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = tap_val(t[c], label_at<true>(src, l, t[c].p00, 1, Lp), label_at<true>(src, l, t[c].p01, 1, Lp),
+                          label_at<true>(src, l, t[c].p10, 1, Lp), label_at<true>(src, l, t[c].p11, 1, Lp));
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&skey[l], f2key(mn));
+      atomicMax(&skey[L + l], f2key(mx));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * L; i += 256) {
+    if (i < L) atomicMin(mm + i, skey[i]);
+    else atomicMax(mm + i, skey[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int L,
+                          int Lp, int H, int W, int out_h, int out_w, const uint32_t* __restrict__ minmax,
+                          uint8_t* __restrict__ masks) {
+  extern __shared__ float smm[];       // [2L] decoded min / max
+  const uint32_t* mm = minmax + (int64_t)blockIdx.y * 2 * L;
+  for (int i = threadIdx.x; i < 2 * L; i += 256) smm[i] = key2f(__ldg(mm + i));
+  __syncthreads();
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= out_h * out_w) return;
+  const int slot = jobs[job_begin + blockIdx.y].out_slot;
+  const float4* src = reinterpret_cast<const float4*>(lab + (int64_t)slot * H * W * Lp);
+  const int l4n = Lp / 4;
+  const int oy = o / out_w, ox = o - oy * out_w;
+  const Tap t = make_tap(oy, ox, H, W, (float)H / (float)out_h, (float)W / (float)out_w);
+  float best = -INFINITY;
+  int arg = 0;
+  for (int l4 = 0; l4 < l4n; ++l4) {
+    const float4 a = __ldg(src + (int64_t)t.p00 * l4n + l4), b = __ldg(src + (int64_t)t.p01 * l4n + l4);
+    const float4 c = __ldg(src + (int64_t)t.p10 * l4n + l4), d = __ldg(src + (int64_t)t.p11 * l4n + l4);
+    const float v4[4] = {tap_val(t, a.x, b.x, c.x, d.x), tap_val(t, a.y, b.y, c.y, d.y),
+                         tap_val(t, a.z, b.z, c.z, d.z), tap_val(t, a.w, b.w, c.w, d.w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int l = 4 * l4 + k;
+      if (l < L) {
+        float v = v4[k];
+        const float mn = smm[l], mx = smm[L + l];
+        if (mx > 0.f) v = __fdiv_rn(v - mn, (mx - mn) + 1e-12f);
+        if (v > best) { best = v; arg = l; }
+      }
+    }
+  }
+  masks[(int64_t)slot * out_h * out_w + o] = (uint8_t)arg;
+}
+
+// min keys are initialised to 0xffffffff and max keys to 0 by init_minmax_kernel
+__global__ void init_minmax_kernel(uint32_t* mm, int n_frames, int L) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n_frames * 2 * L) mm[i] = (i % (2 * L)) < L ? 0xffffffffu : 0u;
+}
+
+int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
+                       int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st) {
+  const int n = job_end - job_begin;
+  if (n <= 0) return FGVC_OK;
+  init_minmax_kernel<<<cdiv(n * 2 * L, 256), 256, 0, st>>>(minmax, n, L);
+  FGVC_LAUNCH_CHECK();
+  dim3 grid(cdiv(out_h * out_w, 256), n), grid_cells(cdiv(H * W, 256), n);
+  decode_minmax_jobs_kernel<<<grid_cells, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w,
+                                                               minmax);
+  FGVC_LAUNCH_CHECK();
+  decode_argmax_jobs_kernel<<<grid, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
+                                                         masks);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
 int launch_decode(const float* src, bool pixmajor, int L, int Lp, int H, int W, int out_h, int out_w,
                   uint32_t* minmax, uint8_t* out, cudaStream_t st) {
   FGVC_CUDA(cudaMemsetAsync(minmax, 0xff, (size_t)L * 4, st));

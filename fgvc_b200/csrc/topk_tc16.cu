@@ -219,28 +219,45 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
       uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
       const uint32_t ring_u32 = smem_u32(ring);
       const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+      // The barrier probes of box it+1 are issued while the last MMAs of box it are still queued in
+      // the tensor pipe, so the pipe does not drain during the ~100-cycle try_wait round trips.
+      if (n_total > 0) {
+        mbar_wait(tempty_bar + 0, tphase0 ^ 1);
+        mbar_wait(full_bar + 0, phase);
+        tc_fence_after();
+      }
       for (int it = 0; it < n_total; ++it) {
-        mbar_wait(tempty_bar + buf, (buf ? tphase1 : tphase0) ^ 1);   // epilogue drained this accumulator
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-        mbar_wait(full_bar + stage, phase);
-        tc_fence_after();
         const uint32_t sa = ring_u32 + (uint32_t)(stage * stage_bytes);
         for (int kc = 0; kc < n_kc; ++kc) {
           const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * T16_STAGE_BYTES)) >> 4);
           const uint32_t a_hi = tmem_base + T16_AHI_COL + kc * 32, a_lo = tmem_base + T16_ALO_COL + kc * 32;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
+            if (ks == 3 && kc == n_kc - 1) break;  // the last K step is issued after the probes below
             const uint64_t o = (uint64_t)(ks * 2);
             umma_f16_ts(d_tmem, a_hi + ks * 8, b + o, idesc2, (kc | ks) != 0);   // [hi*hi | hi*lo]
             umma_f16_ts(d_tmem + N, a_lo + ks * 8, b + o, idesc1, 1);            // += lo*hi
           }
         }
+        const int nstage = (stage + 1 == n_stages) ? 0 : stage + 1;
+        const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
+        const int nbuf = buf ^ 1;
+        if (it + 1 < n_total) {
+          mbar_wait(tempty_bar + nbuf, (nbuf ? tphase1 : tphase0) ^ 1);   // epilogue drained the other accumulator
+          mbar_wait(full_bar + nstage, nphase);                           // next key box landed
+          tc_fence_after();
+        }
+        {
+          const int kc = n_kc - 1;
+          const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * T16_STAGE_BYTES)) >> 4);
+          umma_f16_ts(d_tmem, tmem_base + T16_AHI_COL + kc * 32 + 24, b + 6, idesc2, 1);
+          umma_f16_ts(d_tmem + N, tmem_base + T16_ALO_COL + kc * 32 + 24, b + 6, idesc1, 1);
+        }
         umma_commit(empty_bar + stage);     // smem stage free once these MMAs retire
         umma_commit(tfull_bar + buf);       // accumulator complete
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
         if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf ^= 1;
+        buf = nbuf; stage = nstage; phase = nphase;
       }
     }
     __syncwarp();

@@ -254,7 +254,7 @@ class MaskClipPropagator:
         self.table.device(device)
         self.maps = torch.empty(T, L, H, W, dtype=torch.float32, device=device)
         self.masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=device)
-        self.scratch = torch.empty(2 * L, dtype=torch.float32, device=device)
+        self.scratch = torch.empty(max(T, 1) * 2 * L, dtype=torch.float32, device=device)
         self.k1_events = None
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 

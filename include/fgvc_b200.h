@@ -165,8 +165,9 @@ FGVC_API int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int
 /* Clip-level tails: the sequential part of the reference loop (vanilla_tracker.py:345-412)
  * enqueued by one call after K0 + K1 ran for the whole clip.  jobs_host = host copy of the
  * job table (the launcher needs each out_slot).
- *  mask tail : per job in [job_begin, job_end) K1b gather -> [optional NCHW copy into maps_nchw[slot]] -> decode into
- *              masks[slot][out_h][out_w];
+ *  mask tail : the K1b gather chain over jobs [job_begin, job_end) (+ optional NCHW copies into
+ *              maps_nchw[slot]), then ONE batched decode of all their frames into
+ *              masks[slot][out_h][out_w]; scratch_minmax: (job_end - job_begin) * 2 * L words;
  *  point tail: per job in [job_begin, job_end) K1b gather -> NCHW (maps_scratch [L][H*W]) ->
  *              K3 into coords[slot][L][2]. */
 FGVC_API int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,

@@ -132,11 +132,19 @@ class JobTable:
         return Job(*self.jobs[i])
 
 
-def pick_groups(n_jobs, H, W, max_mem, tile=64):
-    """Split memory lists so that a short job list still fills 148 SMs about twice."""
-    ctas = n_jobs * ((H * W + tile - 1) // tile)
-    g = (2 * NUM_SMS + ctas - 1) // ctas
-    return int(max(1, min(g, max_mem, 64)))
+def pick_groups(n_jobs, H, W, max_mem, max_groups=4):
+    """Number of memory groups per job for one K1 launch.  A CTA is one (query tile, job, group);
+    one CTA runs per SM, so a launch takes ceil(ctas / 148) rounds of (1/groups) of a job's memory
+    list.  Pick the split with the fewest effective rounds (short launches suffer most from a
+    partially filled last wave); ties go to fewer groups (less per-CTA set-up and merging)."""
+    ctas = n_jobs * (-(-H // 8)) * (-(-W // 16))          # 128-query tiles (8x16 or 16x8 pixels)
+    best, best_cost = 1, None
+    for g in range(1, max(1, min(max_groups, max_mem)) + 1):
+        rounds = -(-ctas * g // NUM_SMS)
+        cost = rounds / g + 0.02 * (g - 1)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = g, cost
+    return best
 
 
 class TopKLists:
@@ -262,17 +270,19 @@ class MaskClipPropagator:
         call("fgvc_decode_masks_pixmajor", ptr(self.labels.buf), t, self.labels.Lp, self.L, self.H, self.W,
              self.out_hw[0], self.out_hw[1], ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
 
-    def _tail(self, j0, j1, want_maps):
+    def _tail(self, j0, j1, want_maps, lists=None):
+        lists = lists or self.lists
         jobs, _, mem_label = self.table.device(self.device)
-        call("fgvc_mask_clip_tail", ptr(self.lists.val), ptr(self.lists.idx), self.lists.K, self.groups,
+        call("fgvc_mask_clip_tail", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups,
              ptr(jobs), ptr(self.jobs_host), j0, j1, ptr(mem_label), self.H, self.W,
              float(self.cfg["temperature"]), ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
              self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None, stream_ptr())
 
-    def _k1(self, j0, j1):
+    def _k1(self, j0, j1, lists=None):
         cfg = self.cfg
+        lists = lists or self.lists
         affinity_topk(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
-                      groups=self.groups, engine=self.engine_id, lists=self.lists, job_range=(j0, j1))
+                      groups=lists.groups, engine=self.engine_id, lists=lists, job_range=(j0, j1))
 
     def run(self, feats, onehot0, events=False, want_maps=True):
         """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks);
@@ -303,6 +313,14 @@ class MaskClipPropagator:
             self._stage = torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
             self._onehot = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
             self._copy = torch.cuda.Stream(device=self.device)
+            self._host_chunk = None
+        if self._host_chunk != chunk_frames:
+            # the chunk launches are short: split the memory lists so that their last wave is full
+            self._host_chunk = chunk_frames
+            self._host_groups = pick_groups(min(chunk_frames, max(1, len(self.table))), self.H, self.W,
+                                            self.table.max_mem) if self.T > 1 else 1
+            self._host_lists = TopKLists(max(1, len(self.table)), self._host_groups, self.H * self.W, cfg["topk"],
+                                         self.device)
         cur = torch.cuda.current_stream()
         self._copy.wait_stream(cur)                       # staging buffers free again
         evs = []
@@ -322,7 +340,7 @@ class MaskClipPropagator:
                 self._decode(0)
             j0, j1 = max(s, 1) - 1, e - 1                 # job t-1 propagates frame t
             if j1 > j0:
-                self._k1(j0, j1)
-                self._tail(j0, j1, False)
+                self._k1(j0, j1, self._host_lists)
+                self._tail(j0, j1, False, self._host_lists)
         masks_host.copy_(self.masks, non_blocking=True)
         return masks_host

@@ -34,25 +34,29 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
                             reinterpret_cast<uint32_t*>(scratch_minmax), masks, (cudaStream_t)stream);
 }
 
-// Point tracking tail: gather + fused up-sample / soft-argmax per frame (K3 reads NCHW maps,
-// staged through `maps_scratch` [L][H*W]); coords[slot][L][2].
+// Point tracking tail: the gather chain over jobs [job_begin, job_end) with an NCHW copy of every
+// propagated frame into maps_nchw[slot][L][H*W], then ONE K3 launch (fused up-sample / soft-argmax)
+// over all (frame, point) maps of the range: coords[slot][L][2].  The out_slots of the range must
+// be consecutive (they are frame indices).
 extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                                     const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                                     int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                                     float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
-                                    int32_t out_w, int32_t coord_topk, float* maps_scratch, float* coords,
+                                    int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
                                     void* stream) {
-  FGVC_CHECK_ARG(jobs_dev && jobs_host && maps_scratch && coords && lab_bank, "fgvc_point_clip_tail: null pointer");
+  FGVC_CHECK_ARG(jobs_dev && jobs_host && maps_nchw && coords && lab_bank, "fgvc_point_clip_tail: null pointer");
+  FGVC_CHECK_ARG(job_end > job_begin, "fgvc_point_clip_tail: empty job range");
   const int n_pix = H * W;
+  const int slot0 = jobs_host[job_begin].out_slot;
   for (int j = job_begin; j < job_end; ++j) {
+    const int slot = jobs_host[j].out_slot;
+    FGVC_CHECK_ARG(slot == slot0 + (j - job_begin), "fgvc_point_clip_tail: out_slots must be consecutive");
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
                                 temperature, lab_bank, Lp, stream);
     if (rc) return rc;
-    const int slot = jobs_host[j].out_slot;
-    rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_scratch, stream);
-    if (rc) return rc;
-    rc = fgvc_heatmap_coords(maps_scratch, L, H, W, out_h, out_w, coord_topk, coords + (int64_t)slot * L * 2, stream);
+    rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
     if (rc) return rc;
   }
-  return FGVC_OK;
+  return fgvc_heatmap_coords(maps_nchw + (int64_t)slot0 * L * n_pix, (job_end - job_begin) * L, H, W, out_h, out_w,
+                             coord_topk, coords + (int64_t)slot0 * L * 2, stream);
 }

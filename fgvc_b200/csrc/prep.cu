@@ -35,23 +35,28 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
   }
   __syncthreads();
   const int64_t slot_off = (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
-  for (int i = threadIdx.x; i < 32 * C; i += 256) {
-    int pp = i / C, c = i - pp * C;
-    int p = p0 + pp;
+  // two consecutive channels per thread: 4-byte (fp16 pair) / 8-byte (fp32 pair) stores
+  const int c2n = C / 2;
+  for (int i = threadIdx.x; i < 32 * c2n; i += 256) {
+    const int pp = i / c2n, c = 2 * (i - pp * c2n);
+    const int p = p0 + pp;
     if (p < n_pix) {
-      float x = __fdiv_rn(tile[c * 33 + pp], inv[pp]);
+      const float x0 = __fdiv_rn(tile[c * 33 + pp], inv[pp]);
+      const float x1 = __fdiv_rn(tile[(c + 1) * 33 + pp], inv[pp]);
       if (FMT == FGVC_BANK_TF32) {
         float* hi = reinterpret_cast<float*>(bank_v) + slot_off;
         float* lo = hi + (int64_t)n_pix * C;
-        float h = tf32_round(x);
-        hi[(int64_t)p * C + c] = h;
-        lo[(int64_t)p * C + c] = x - h;
+        const float h0 = tf32_round(x0), h1 = tf32_round(x1);
+        *reinterpret_cast<float2*>(hi + (int64_t)p * C + c) = make_float2(h0, h1);
+        *reinterpret_cast<float2*>(lo + (int64_t)p * C + c) = make_float2(x0 - h0, x1 - h1);
       } else {
         __half* hi = reinterpret_cast<__half*>(bank_v) + slot_off;
         __half* lo = hi + (int64_t)n_pix * C;
-        __half h = __float2half_rn(x);
-        hi[(int64_t)p * C + c] = h;
-        lo[(int64_t)p * C + c] = __float2half_rn((x - __half2float(h)) * FGVC_F16_LO_SCALE);
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        *reinterpret_cast<__half2*>(hi + (int64_t)p * C + c) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(lo + (int64_t)p * C + c) =
+            __halves2half2(__float2half_rn((x0 - __half2float(h0)) * FGVC_F16_LO_SCALE),
+                           __float2half_rn((x1 - __half2float(h1)) * FGVC_F16_LO_SCALE));
       }
     }
   }

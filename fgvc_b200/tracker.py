@@ -122,7 +122,7 @@ class VanillaTracker(nn.Module):
             coords = torch.zeros(T, P, 2, dtype=torch.float32, device=dev)
             coords[t0] = engine.gaussian_coords(pts, (h, w))
             if T - t0 > 1:
-                scratch = torch.empty(P, Hf, Wf, dtype=torch.float32, device=dev)
+                scratch = torch.empty(T, P, Hf, Wf, dtype=torch.float32, device=dev)   # NCHW maps of every frame
                 _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
                           _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
                           float(cfg.temperature), _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),

@@ -168,8 +168,9 @@ FGVC_API int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int
  *  mask tail : the K1b gather chain over jobs [job_begin, job_end) (+ optional NCHW copies into
  *              maps_nchw[slot]), then ONE batched decode of all their frames into
  *              masks[slot][out_h][out_w]; scratch_minmax: (job_end - job_begin) * 2 * L words;
- *  point tail: per job in [job_begin, job_end) K1b gather -> NCHW (maps_scratch [L][H*W]) ->
- *              K3 into coords[slot][L][2]. */
+ *  point tail: the K1b gather chain over jobs [job_begin, job_end) with an NCHW copy of every frame
+ *              into maps_nchw[slot][L][H*W], then ONE K3 launch over all their (frame, point) maps
+ *              into coords[slot][L][2]; the out_slots of the range must be consecutive. */
 FGVC_API int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                         const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                         int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
@@ -180,7 +181,7 @@ FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx
                          const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                          int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                          float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
-                         int32_t out_w, int32_t coord_topk, float* maps_scratch, float* coords,
+                         int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
                          void* stream);
 
 /* K2 -- coarse-to-fine propagation (local_attention.py:721-880), single query frame.

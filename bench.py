@@ -61,6 +61,29 @@ def algorithmic_work():
     return dict(flops_per_step=flops, in_mask_pairs=pairs, mem_entries=entries)
 
 
+def k1_traffic(split):
+    """DRAM bytes of one K1 launch of this workload from the committed ncu capture (or None)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[split]
+        return d["bytes"], d["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+def algorithmic_bytes():
+    """per propagated frame 4*[C*Nq + C*Nk*T_u] feature bytes (fp32-equivalent: every unique
+    memory frame and the query frame read once) -- summed over the clip's 63 jobs; the top-k lists
+    (8*k*Nq per job) are what K1 writes."""
+    H, W = WORK["feat_hw"]
+    C, T, k = WORK["channels"], WORK["clip_frames"], WORK["topk"]
+    n = H * W
+    total = 0
+    for t in range(1, T):
+        uniq = min(t, WORK["precede_frames"]) + (0 if t <= WORK["precede_frames"] else 1)
+        total += 4 * (C * n + C * n * uniq) + 8 * k * n
+    return total
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -215,6 +238,7 @@ def run_ours(args):
         peak = pk["bf16"] / 3.0 if split == "f16" else pk["bf16"] / 2.0 / 3.0
         kname = "affinity_topk_tc16_kernel (K1, fp16 three-term split)" if split == "f16" else \
             "affinity_topk_tc_kernel (K1, 3xTF32)"
+        traffic, traffic_src = k1_traffic(split)
         out = dict(metric="propagated frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                    warmup=n_warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype=("f16x3" if split == "f16" else "tf32x3") + " split, fp32 accumulate (fp32-faithful)",
@@ -224,7 +248,8 @@ def run_ours(args):
                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                    gpu_launches=int(launches),
                    roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak,
-                                 unit="TFLOP/s", frac=achieved / peak, traffic=None, k1_ms=k1,
+                                 unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
+                                 algorithmic_bytes=algorithmic_bytes(), k1_ms=k1,
                                  k1_share_of_step=k1 / (ms / args.steps),
                                  peak_source=f"{pk['src']} bf16 sustained {pk['bf16']} TF/s" + (" / 3 (three fp16 MMAs per MAC)" if split == "f16"
                                              else " / 2 (tf32) / 3 (3xTF32)"),

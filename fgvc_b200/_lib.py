@@ -14,6 +14,7 @@ MASK_CIRCLE, MASK_SQUARE = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 BANK_TF32, BANK_F16 = 0, 1
 MEM_UNMASKED = 0x40000000
+WEIGHT_COSINE, SIM_L2 = 1, 2
 
 
 class FgvcError(RuntimeError):
@@ -43,13 +44,13 @@ SIGNATURES = {
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
     "fgvc_affinity_topk": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
     "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
-    "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, P, I, P]),
+    "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, I, P, I, P]),
     "fgvc_heatmap_coords": (I, [P, I, I, I, I, I, I, P, P]),
     "fgvc_gaussian_coords": (I, [P, I, I, I, F, I, P, P]),
     "fgvc_decode_masks": (I, [P, I, I, I, I, I, P, P, P]),
     "fgvc_decode_masks_pixmajor": (I, [P, I, I, I, I, I, I, I, P, P, P]),
-    "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, P, P, P, P]),
-    "fgvc_point_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, P, I, I, I, I, I, P, P, P]),
+    "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, I, P, I, I, I, I, P, P, P, P]),
+    "fgvc_point_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, I, P, I, I, I, I, I, P, P, P]),
     "fgvc_c2f_propagate": (I, [P, I, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, I, P]),
 }
 

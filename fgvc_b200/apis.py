@@ -200,3 +200,56 @@ def collect_results_cpu(result_part, size, tmpdir=None):
     if rank != 0:
         return None
     return _interleave([pickle.loads(b) for b in gathered], size)
+
+
+# ------------------------------------------------------------------ single long video: shard the points
+def point_shard(n_points, rank, world):
+    """Contiguous slice of the tracked points owned by ``rank`` (label channels
+    never mix, so a long video shards by point with no per-frame exchange)."""
+    lo = (n_points * rank) // world
+    hi = (n_points * (rank + 1)) // world
+    return lo, hi
+
+
+def sharded_forward_test(model, rgbs, query_points, trajectories, visibilities, **kw):
+    """``forward_test`` of one (long) video with the tracked points sharded across the ranks of the
+    default process group.  Every rank encodes the clip and recomputes the (label-independent)
+    affinity top-k; it propagates only its slice of the points.  The only collective is one
+    ``all_gather`` of the ``[T, P_rank, 2]`` tracks.  Returns the reference's 5-tuple
+    (vanilla_tracker.py:227-303) on every rank, identical to the un-sharded call."""
+    rank, world = get_dist_info()
+    if world == 1:
+        return model(test_mode=True, rgbs=rgbs, query_points=query_points, trajectories=trajectories,
+                     visibilities=visibilities, **kw)
+    assert rgbs.shape[0] == 1
+    B, T = rgbs.shape[:2]
+    P = query_points.shape[1]
+    lo, hi = point_shard(P, rank, world)
+    grouped = bool(model.test_cfg.get("with_first", False))
+    qp = query_points[:, lo:hi]
+    out = model(test_mode=True, rgbs=rgbs, query_points=qp, trajectories=trajectories[:, :, lo:hi],
+                visibilities=visibilities[:, :, lo:hi], **kw) if hi > lo else None
+    # undo the per-shard re-ordering by query frame so that shards concatenate in the original order
+    per = max(point_shard(P, r, world)[1] - point_shard(P, r, world)[0] for r in range(world))
+    dev = out[2].device if out is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                 if dist.get_backend() == "nccl" else torch.device("cpu"))
+    dtype = torch.float32 if grouped else torch.float64
+    local = torch.zeros(T, per, 2, dtype=dtype, device=dev)
+    if out is not None:
+        pred = out[2][0]
+        if grouped:
+            perm = torch.argsort(qp[0, :, 0].to(dev), stable=True)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel(), device=dev)
+            pred = pred[:, inv]
+        local[:, : hi - lo] = pred.to(dtype)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local)
+    full = torch.cat([parts[r][:, : point_shard(P, r, world)[1] - point_shard(P, r, world)[0]] for r in range(world)],
+                     dim=1)[None]
+    query_points, trajectories, visibilities = (x.to(dev) for x in (query_points, trajectories, visibilities))
+    if not grouped:
+        return trajectories, visibilities, full, torch.zeros_like(visibilities), query_points
+    gperm = torch.argsort(query_points[0, :, 0], stable=True)
+    return (trajectories[:, :, gperm], visibilities[:, :, gperm], full[:, :, gperm].to(trajectories.dtype),
+            torch.zeros_like(visibilities), query_points[:, gperm])

@@ -10,7 +10,7 @@ using namespace fgvc;
 extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                                    const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                                    int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
-                                   float temperature,
+                                   float temperature, int32_t flags,
                                    float* lab_bank, int32_t Lp, int32_t L, int32_t out_h, int32_t out_w,
                                    float* scratch_minmax, uint8_t* masks, float* maps_nchw, void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && masks && scratch_minmax && lab_bank, "fgvc_mask_clip_tail: null pointer");
@@ -21,7 +21,7 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
   // the recurrence lives only in the gather: run the chain first ...
   for (int j = job_begin; j < job_end; ++j) {
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
-                                temperature, lab_bank, Lp, stream);
+                                temperature, flags, lab_bank, Lp, stream);
     if (rc) return rc;
     if (maps_nchw) {
       const int slot = jobs_host[j].out_slot;
@@ -41,7 +41,7 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
 extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                                     const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                                     int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
-                                    float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
+                                    float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
                                     int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
                                     void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && maps_nchw && coords && lab_bank, "fgvc_point_clip_tail: null pointer");
@@ -52,7 +52,7 @@ extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_i
     const int slot = jobs_host[j].out_slot;
     FGVC_CHECK_ARG(slot == slot0 + (j - job_begin), "fgvc_point_clip_tail: out_slots must be consecutive");
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
-                                temperature, lab_bank, Lp, stream);
+                                temperature, flags, lab_bank, Lp, stream);
     if (rc) return rc;
     rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
     if (rc) return rc;

@@ -174,13 +174,32 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     return lists
 
 
-def gather_labels(lists, table, job_begin, job_end, labels, temperature):
+def sim_params(cfg_or_none, C, temperature, mode="softmax", sim_mode="dot_product", normalize=True):
+    """(temperature, flags) for fgvc_gather_labels.  ``sim_mode='l2-distance'`` (local_attention.py:324-327)
+    is (2ab - |a|^2)/sqrt(C): on L2-normalised features |a|^2 = 1, so it is a monotone map of the cosine --
+    same top-k -- applied to the winners only; without normalisation it would need key norms: not built."""
+    flags = 0
+    if mode == "cosine":
+        flags |= _lib.WEIGHT_COSINE
+    elif mode != "softmax":
+        raise ValueError(mode)
+    if sim_mode == "l2-distance":
+        if not normalize:
+            raise NotImplementedError("sim_mode='l2-distance' needs normalize=True (unit vectors)")
+        flags |= _lib.SIM_L2
+        temperature = float(C) ** 0.5
+    elif sim_mode != "dot_product":
+        raise AssertionError(sim_mode)
+    return float(temperature), flags
+
+
+def gather_labels(lists, table, job_begin, job_end, labels, temperature, flags=0):
     """K1b for jobs [job_begin, job_end): writes each job's out_slot of ``labels``."""
     dev = labels.buf.device
     jobs, _, mem_label = table.device(dev)
     call("fgvc_gather_labels", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups, ptr(jobs), int(job_begin),
-         int(job_end), ptr(mem_label), labels.H * labels.W, float(temperature), ptr(labels.buf), labels.Lp,
-         stream_ptr())
+         int(job_end), ptr(mem_label), labels.H * labels.W, float(temperature), int(flags), ptr(labels.buf),
+         labels.Lp, stream_ptr())
 
 
 def heatmap_coords(maps, out_hw, topk=5):
@@ -264,6 +283,8 @@ class MaskClipPropagator:
         self.masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=device)
         self.scratch = torch.empty(max(T, 1) * 2 * L, dtype=torch.float32, device=device)
         self.k1_events = None
+        self.temperature, self.flags = sim_params(cfg, C, cfg["temperature"], sim_mode=cfg.get("sim_mode", "dot_product"),
+                                                  normalize=cfg.get("with_norm", True))
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 
     def _decode(self, t):
@@ -275,7 +296,7 @@ class MaskClipPropagator:
         jobs, _, mem_label = self.table.device(self.device)
         call("fgvc_mask_clip_tail", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups,
              ptr(jobs), ptr(self.jobs_host), j0, j1, ptr(mem_label), self.H, self.W,
-             float(self.cfg["temperature"]), ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
+             self.temperature, self.flags, ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
              self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None, stream_ptr())
 
     def _k1(self, j0, j1, lists=None):

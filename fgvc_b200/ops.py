@@ -8,8 +8,8 @@ Reference interfaces (paths relative to the FGVC repository):
   spatial_neighbor                mmpt/models/common/affinity_utils.py:75-112
 
 Differences, all loud: N must be 1 (the reference driver asserts it and its gather
-indexes batch 0 only, local_attention.py:360-362); ``sim_mode='l2-distance'``,
-``mode='cosine'`` and ``topk=None`` raise NotImplementedError; ``step`` is accepted and
+indexes batch 0 only, local_attention.py:360-362); ``topk=None`` (dense soft-max), ``topk > 16`` and
+``sim_mode='l2-distance'`` without normalisation raise NotImplementedError; ``step`` is accepted and
 ignored (nothing is chunked: the affinity never exists in HBM); a ``mask`` tensor must be
 one that ``spatial_neighbor`` produces (its radius is recovered and verified), because the
 kernels evaluate the mask analytically.  There is no CPU fallback.
@@ -97,10 +97,7 @@ def _check_common(query, key, value, mode, sim_mode, topk):
     assert query.size(0) == key.size(0) == value.size(0)
     if query.size(0) != 1:
         raise NotImplementedError("batch size must be 1 (as in the reference driver, vanilla_tracker.py:134)")
-    if mode != "softmax":
-        raise NotImplementedError("mode='cosine' is not built")
-    if sim_mode != "dot_product":
-        raise NotImplementedError("sim_mode='l2-distance' is not built")
+    assert sim_mode in ["dot_product", "l2-distance"]
     if topk is None:
         raise NotImplementedError("topk=None (dense soft-max) is not built")
     if not (1 <= topk <= 16):
@@ -112,12 +109,13 @@ def _check_common(query, key, value, mode, sim_mode, topk):
 
 
 def _propagate(query, key, value, radius, mask_mode, temperature, topk, normalize, non_mask_len, engine_id,
-               groups=None, split=None):
+               groups=None, split=None, mode="softmax", sim_mode="dot_product"):
     C, Hq, Wq = query.shape[1:]
     T, Hk, Wk = key.shape[2:]
     L = value.size(1)
     if (Hq, Wq) != (Hk, Wk):
         raise NotImplementedError("query and key grids must match")
+    temperature, flags = engine.sim_params(None, C, temperature, mode, sim_mode, normalize)
     dev = query.device
     query = query.float().contiguous()
     key = key.float().contiguous()
@@ -134,7 +132,7 @@ def _propagate(query, key, value, radius, mask_mode, temperature, topk, normaliz
     table.add(T, list(range(T)), list(range(T)), T, unmasked=non_mask_len if radius is not None else T)
     r = radius if radius is not None else 1
     lists = engine.affinity_topk(feats, table, r, topk, mask_mode, groups=groups, engine=engine_id)
-    engine.gather_labels(lists, table, 0, 1, labels, temperature)
+    engine.gather_labels(lists, table, 0, 1, labels, temperature, flags)
     return labels.get_nchw(T).view(1, L, Hq, Wq)
 
 
@@ -156,7 +154,7 @@ def masked_attention_efficient(query, key, value, mask, temperature=1, topk=None
     else:
         mask_mode, radius = _mask_spec(mask, key.shape[3], key.shape[4], query.shape[2], query.shape[3])
     return _propagate(query, key, value, radius, mask_mode, temperature, topk, normalize, non_mask_len, engine_id,
-                      split=split)
+                      split=split, mode=mode, sim_mode=sim_mode)
 
 
 def masked_attention_efficient_v2(query, key, value, radius, temperature=1, topk=None, normalize=True, step=32,
@@ -172,7 +170,7 @@ def masked_attention_efficient_v2(query, key, value, radius, temperature=1, topk
     assert value.ndim == key.ndim == 5
     assert 0 <= non_mask_len < key.size(2)
     return _propagate(query, key, value, int(radius), "circle", temperature, topk, normalize, 0, engine_id,
-                      split=split)
+                      split=split, mode=mode)
 
 
 def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask, temperature=1, topk=None,
@@ -181,6 +179,8 @@ def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask
     """Coarse-to-fine propagation (local_attention.py:721-880).  ``value`` lives on the FINE
     grid [1,L,T,s*Hk,s*Wk]; the output on the COARSE query grid [1,L,Hq,Wq]."""
     _check_common(query, key, value, mode, sim_mode, topk)
+    if mode != "softmax" or sim_mode != "dot_product":
+        raise NotImplementedError("c2f is built for mode='softmax', sim_mode='dot_product'")
     if key.ndim == 4:
         key, value, key_fine = key.unsqueeze(2), value.unsqueeze(2), key_fine.unsqueeze(2)
     assert value.ndim == key.ndim == 5
@@ -218,3 +218,52 @@ def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask
     out = engine.c2f_propagate(coarse, fine, table, 0, labels, radius, radius_fine, topk, temperature, mask_mode,
                                engine_id)
     return out[:, :L].t().reshape(1, L, Hq, Wq).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Legacy VFS-style utilities (mmpt/models/common/affinity_utils.py:6-73).  Nothing in the reference
+# calls them; they are kept importable with the same signatures and semantics ("subtract the k-th
+# largest, clamp, L1-renormalise" top-k, unlike the path above).  Plain device-agnostic torch ops:
+# they are API surface, not part of the accelerated hot path.
+def compute_affinity(src_img, dst_img, temperature=1., normalize=True, softmax_dim=None, mask=None):
+    batches, channels = src_img.shape[:2]
+    src_feat = src_img.reshape(batches, channels, -1)
+    dst_feat = dst_img.reshape(batches, channels, -1)
+    if normalize:
+        src_feat = torch.nn.functional.normalize(src_feat, p=2, dim=1)
+        dst_feat = torch.nn.functional.normalize(dst_feat, p=2, dim=1)
+    affinity = torch.bmm(src_feat.permute(0, 2, 1).contiguous(), dst_feat.contiguous()) / temperature
+    if mask is not None:
+        affinity = affinity.masked_fill(~mask.bool(), float("-inf"))
+    if softmax_dim is not None:
+        affinity = affinity.softmax(dim=softmax_dim)
+    if mask is not None:
+        affinity = torch.nan_to_num(affinity, nan=0.0)
+    return affinity
+
+
+def _legacy_topk(affinity, topk, shape):
+    kth = affinity.topk(dim=1, k=topk)[0][:, topk - 1].view(*shape)
+    affinity = (affinity - kth).clamp(min=0)
+    return affinity / affinity.sum(keepdim=True, dim=1).clamp(min=1e-12)
+
+
+def propagate(img, affinity, topk=None):
+    batches, channels, height, width = img.size()
+    if topk is not None:
+        affinity = _legacy_topk(affinity, topk, (batches, 1, height * width))
+    new_img = torch.bmm(img.reshape(batches, channels, -1), affinity.contiguous())
+    return new_img.reshape(batches, channels, height, width)
+
+
+def propagate_temporal(imgs, affinities, topk=None):
+    batches, channels, clip_len, height, width = imgs.size()
+    assert affinities.size(0) == batches
+    assert affinities.size(1) == clip_len
+    assert affinities.size(2) == height * width
+    assert affinities.size(2) == affinities.size(3)
+    affinities = affinities.reshape(batches, clip_len * height * width, height * width)
+    if topk is not None:
+        affinities = _legacy_topk(affinities, topk, (batches, 1, height * width))
+    new_imgs = torch.bmm(imgs.reshape(batches, channels, -1), affinities)
+    return new_imgs.reshape(batches, channels, height, width)

@@ -93,8 +93,8 @@ class VanillaTracker(nn.Module):
         if nr is None and not v1:
             raise TypeError("test_mode v2 needs neighbor_range (the reference computes neighbor_range//2)")
         unmasked_first = 0 if (cfg.get("with_first_neighbor", True) or not v1) else 1
-        if cfg.get("sim_mode", "dot_product") != "dot_product":
-            raise NotImplementedError("sim_mode='l2-distance' is not built")
+        temperature, flags = engine.sim_params(cfg, C, cfg.temperature, sim_mode=cfg.get("sim_mode", "dot_product"),
+                                               normalize=cfg.get("with_norm", True))
 
         bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
         bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
@@ -125,7 +125,7 @@ class VanillaTracker(nn.Module):
                 scratch = torch.empty(T, P, Hf, Wf, dtype=torch.float32, device=dev)   # NCHW maps of every frame
                 _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
                           _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
-                          float(cfg.temperature), _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
+                          temperature, flags, _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
                           _lib.ptr(coords), _lib.stream_ptr())
             outs.append(coords.double())
         return outs

@@ -79,6 +79,11 @@ typedef struct fgvc_job {
   int32_t out_slot;   /* label-bank slot written by fgvc_gather_labels */
 } fgvc_job;
 
+/* fgvc_gather_labels flags */
+#define FGVC_WEIGHT_COSINE 1 /* weights = clamp(a, 0)^2 instead of softmax(a)   (mode='cosine', local_attention.py:371) */
+#define FGVC_SIM_L2 2        /* a = (2 cos - 1) / temperature with temperature := sqrt(C)
+                                (sim_mode='l2-distance' on normalised features, local_attention.py:324-327) */
+
 #define FGVC_MEM_UNMASKED 0x40000000 /* OR into mem_feat_slot: radius mask not applied
                                         (the first non_mask_len frames, local_attention.py:347) */
 
@@ -139,7 +144,7 @@ FGVC_API int fgvc_debug_affinity_boxes(const void* feat_bank, int32_t bank_forma
  * jobs of one time step across clips: they must not read each other's out_slot). */
 FGVC_API int fgvc_gather_labels(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                        const fgvc_job* jobs, int32_t job_begin, int32_t job_end,
-                       const int32_t* mem_label_slot, int32_t n_pix, float temperature,
+                       const int32_t* mem_label_slot, int32_t n_pix, float temperature, int32_t flags,
                        float* lab_bank, int32_t Lp, void* stream);
 
 /* K3 -- F.interpolate(bilinear, align_corners=False) to (out_h,out_w) fused with img2coord
@@ -174,15 +179,15 @@ FGVC_API int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int
 FGVC_API int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                         const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                         int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
-                        float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
-                        int32_t out_w, float* scratch_minmax, uint8_t* masks, float* maps_nchw,
-                        void* stream);
+                        float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L,
+                        int32_t out_h, int32_t out_w, float* scratch_minmax, uint8_t* masks,
+                        float* maps_nchw, void* stream);
 FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                          const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                          int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
-                         float temperature, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
-                         int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
-                         void* stream);
+                         float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L,
+                         int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
+                         float* coords, void* stream);
 
 /* K2 -- coarse-to-fine propagation (local_attention.py:721-880), single query frame.
  * Coarse stage = per-memory-frame masked argmax on the coarse bank (K1 with K=1 per

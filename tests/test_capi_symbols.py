@@ -36,7 +36,7 @@ def test_errors_are_reported_not_thrown():
     from fgvc_b200 import _lib
     lib = _lib.load()
     # null pointers are rejected before any CUDA call
-    rc = lib.fgvc_gather_labels(None, None, 10, 1, None, 0, 1, None, 16, 0.07, None, 4, None)
+    rc = lib.fgvc_gather_labels(None, None, 10, 1, None, 0, 1, None, 16, 0.07, 0, None, 4, None)
     assert rc == -1
     assert b"null pointer" in lib.fgvc_last_error()
     with pytest.raises(_lib.FgvcError):

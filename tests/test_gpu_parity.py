@@ -122,6 +122,9 @@ CASES = [
     (20, 24, 64, 3, 4, 3, 10, 1, "circle"),      # first frame unmasked
     (17, 21, 64, 2, 6, 3, 7, 0, "square"),       # square window
     (3, 5, 32, 2, 2, 12, 10, 0, "circle"),       # map smaller than the radius
+    (22, 37, 128, 3, 6, 7, 10, 1, "circle"),     # C = 128, first frame unmasked (whole-frame box list)
+    (18, 26, 192, 2, 9, 20, 16, 0, "circle"),    # C = 192, radius beyond the map, K = 16
+    (40, 24, 256, 2, 3, 6, 10, 0, "square"),     # C = 256, tall map, square window
 ]
 
 
@@ -415,6 +418,27 @@ def test_clip_host_pipeline_equals_resident_run():
     assert float((err > TOL).float().mean()) <= 2e-3
 
 
+@pytest.mark.parametrize("engine", ["simt", "tc16"])
+@pytest.mark.parametrize("mode,sim_mode", [("cosine", "dot_product"), ("softmax", "l2-distance"), ("cosine", "l2-distance")])
+def test_weight_and_similarity_variants(mode, sim_mode, engine):
+    """mode='cosine' (local_attention.py:371) and sim_mode='l2-distance' (:324-327) against the port."""
+    import fgvc_b200
+    g = torch.Generator().manual_seed(13)
+    H, W, C, T, L = 14, 18, 64, 3, 4
+    f = _coherent(g, T + 1, C, H, W)
+    q, k = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+    v = torch.rand(1, L, T, H, W, generator=g)
+    mask = fgvc_b200.spatial_neighbor(1, H, W, 8, "cuda", torch.float32)
+    got = fgvc_b200.masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), mask, temperature=0.07, topk=10,
+                                               mode=mode, sim_mode=sim_mode, **_eng(engine))
+    want = O.propagate_port(q, k, v, mask=O.neighbor_mask(H, W, 8), temperature=0.07, topk=10, mode=mode,
+                            sim_mode=sim_mode)
+    ex = O.propagate_exact(q, k, v, radius=4, temperature=0.07, topk=10)
+    clear = (ex["gap"] > GAP_EPS).view(1, 1, H, W)
+    scale = max(1.0, float(want.abs().max()))
+    assert float(((got.cpu() - want).abs() * clear).max()) < 1e-4 * scale
+
+
 def test_raw_c_abi_as_in_integration_md():
     """the C ABI driven with nothing but ctypes + device pointers."""
     import ctypes
@@ -443,7 +467,7 @@ def test_raw_c_abi_as_in_integration_md():
                                 5, 0, K, 1, P(val.data_ptr()), P(idx.data_ptr()), 0, st)
     assert rc == 0, lib.fgvc_last_error()
     rc = lib.fgvc_gather_labels(P(val.data_ptr()), P(idx.data_ptr()), K, 1, P(jobs.data_ptr()), 0, 1,
-                                P(mem_lab.data_ptr()), H * W, ctypes.c_float(0.07), P(labels.data_ptr()), 8, st)
+                                P(mem_lab.data_ptr()), H * W, ctypes.c_float(0.07), 0, P(labels.data_ptr()), 8, st)
     assert rc == 0, lib.fgvc_last_error()
     torch.cuda.synchronize()
     got = labels[T].t().reshape(1, L, H, W)

@@ -77,9 +77,10 @@ def test_unsupported_modes_raise_loudly():
     with pytest.raises(NotImplementedError):
         ops.masked_attention_efficient(q, k, v, None, topk=None)
     with pytest.raises(NotImplementedError):
-        ops.masked_attention_efficient(q, k, v, None, topk=5, mode="cosine")
+        ops.masked_attention_efficient(q, k, v, None, topk=17)
     with pytest.raises(NotImplementedError):
-        ops.masked_attention_efficient(q, k, v, None, topk=5, sim_mode="l2-distance")
+        engine.sim_params(None, 32, 0.07, sim_mode="l2-distance", normalize=False)
+    assert engine.sim_params(None, 64, 0.07, mode="cosine", sim_mode="l2-distance") == (8.0, 3)
     with pytest.raises(AssertionError):
         ops.masked_attention_efficient(q, k, v, None, topk=5, mode="bogus")
 
@@ -133,3 +134,67 @@ def test_multi_gpu_test_world2_gloo(gpu_collect):
     assert [g[2] for g in got] == [f"video{i}" for i in range(5)]          # reference order, padding cut
     assert [g[0] for g in got] == [float(i) for i in range(5)]
     assert got[3][1] == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_legacy_utilities_match_golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "legacy.npz"))
+    a, b, img = (torch.from_numpy(d[k]) for k in ("a", "b", "img"))
+    aff = ops.compute_affinity(a, b, temperature=0.07, softmax_dim=1)
+    assert torch.allclose(aff, torch.from_numpy(d["aff"]), atol=1e-6)
+    assert torch.allclose(ops.propagate(img, aff, topk=4), torch.from_numpy(d["prop"]), atol=1e-5)
+    vid = torch.stack([img, img], dim=2)
+    affs = torch.stack([aff, aff], dim=1)
+    want = O.propagate_legacy_port(torch.cat([img, img], dim=0)[:2], aff, topk=None)   # shape check only
+    out = ops.propagate_temporal(vid, affs, topk=None)
+    assert out.shape == img.shape and want.shape == img.shape
+    assert torch.allclose(out, 2 * ops.propagate(img, aff), atol=1e-5)
+
+
+class _FakeTracker(torch.nn.Module):
+    """forward_test contract of the tracker with a deterministic per-point 'track'."""
+
+    def __init__(self, with_first):
+        super().__init__()
+        self.test_cfg = dict(with_first=with_first)
+
+    def forward(self, test_mode=True, rgbs=None, query_points=None, trajectories=None, visibilities=None):
+        T, P = rgbs.shape[1], query_points.shape[1]
+        t = torch.arange(T, dtype=torch.float64).view(T, 1, 1)
+        pred = (query_points[0, :, 1:].double().view(1, P, 2) + t)[None]          # x+t, y+t
+        if not self.test_cfg["with_first"]:
+            return trajectories, visibilities, pred, torch.zeros_like(visibilities), query_points
+        perm = torch.argsort(query_points[0, :, 0], stable=True)
+        return (trajectories[:, :, perm], visibilities[:, :, perm], pred[:, :, perm].float(),
+                torch.zeros_like(visibilities), query_points[:, perm])
+
+
+def _shard_worker(rank, world, port, with_first, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    T, P = 4, 7
+    rgbs = torch.zeros(1, T, 3, 8, 8)
+    qp = torch.cat([torch.randint(0, 3, (1, P, 1), generator=g).float(), torch.rand(1, P, 2, generator=g) * 8], dim=2)
+    traj, vis = torch.rand(1, T, P, 2, generator=g), torch.zeros(1, T, P)
+    model = _FakeTracker(with_first)
+    got = apis.sharded_forward_test(model, rgbs, qp, traj, vis)
+    want = model(test_mode=True, rgbs=rgbs, query_points=qp, trajectories=traj, visibilities=vis)
+    ok = all(torch.allclose(a.double(), b.double()) for a, b in zip(got, want))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("with_first", [False, True])
+def test_point_sharded_forward_test_world2_gloo(with_first):
+    assert apis.point_shard(7, 0, 2) == (0, 3) and apis.point_shard(7, 1, 2) == (3, 7)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, 29531 + int(with_first), with_first, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -48,6 +48,7 @@ struct Tc16Params {
   float* dbg;
   int32_t* dbg_meta;
   int dbg_max_boxes;
+  int exp_flags;             // experiments (FGVC_TC16_EXP env): 1 = skip the candidate scan, 2 = skip TMEM loads too
 };
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -321,7 +322,7 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
           if (hi >= lo) bits = (2u << hi) - (1u << lo);
         }
         const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes && row < p.BH;
-        const bool doit = __any_sync(0xffffffffu, bits != 0) || dump;    // warp-uniform
+        const bool doit = (__any_sync(0xffffffffu, bits != 0) || dump) && !(p.exp_flags & 2);    // warp-uniform
         mbar_wait_sleep(tfull_bar + buf, buf ? tph1 : tph0);
         tc_fence_after();
         uint32_t r1[16], r2[16];
@@ -351,7 +352,7 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
             }
           }
           // candidates = in-mask elements above the running K-th value
-          const float thr0 = top.thr();
+          const float thr0 = (p.exp_flags & 1) ? INFINITY : top.thr();
           uint32_t cand = 0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
@@ -467,6 +468,8 @@ int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C
   p.tiles_x = cdiv(W, p.QW);
   p.jobs = jobs; p.mem_feat = mem_feat; p.tv = tv; p.ti = ti;
   p.dbg = dbg; p.dbg_meta = dbg_meta; p.dbg_max_boxes = dbg_max_boxes;
+  static const int exp_flags = getenv("FGVC_TC16_EXP") ? atoi(getenv("FGVC_TC16_EXP")) : 0;   // perf experiments only
+  p.exp_flags = exp_flags;
   FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 f16 engine: radius %d too large", radius);
   FGVC_CHECK_ARG(cdiv(H, p.BH) * cdiv(W, 16) <= T16_MAX_BOXES && H < 65536 && W < 65536,
                  "tcgen05 f16 engine: %dx%d map has too many key boxes", H, W);

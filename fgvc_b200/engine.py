@@ -147,6 +147,36 @@ def pick_groups(n_jobs, H, W, max_mem, max_groups=4):
     return best
 
 
+def plan_chunks(n_jobs, tiles, copy_ratio=0.75, launch_cost=0.4):
+    """Split jobs 0..n_jobs-1 into consecutive chunks for the host pipeline.  Chunk i's K1 launch
+    (chunk_jobs * tiles CTAs, one CTA per SM => whole rounds) can start once its frames have been copied
+    (copies are issued back to back on the copy stream) and the previous chunk has finished.  Dynamic
+    programme over cut positions minimising the finish time; unit = compute time of one job at full
+    efficiency, ``copy_ratio`` = copy time of one frame in that unit, ``launch_cost`` = per-chunk overhead
+    (K0 + tail launches, pipeline fill)."""
+    jobs_per_round = NUM_SMS / float(tiles)
+
+    def compute(n):
+        return -(-n * tiles // NUM_SMS) * jobs_per_round + launch_cost
+
+    INF = float("inf")
+    best = [(INF, None)] * (n_jobs + 1)
+    best[0] = (0.0, None)
+    for end in range(1, n_jobs + 1):
+        copied = copy_ratio * (end + 1)                    # frames 0..end are on the device
+        for start in range(0, end):
+            c = max(copied, best[start][0]) + compute(end - start)
+            if c < best[end][0]:
+                best[end] = (c, start)
+    cuts, e = [], n_jobs
+    while e > 0:
+        s0 = best[e][1]
+        cuts.append((s0, e))
+        e = s0
+    cuts.reverse()
+    return cuts
+
+
 class TopKLists:
     def __init__(self, n_jobs, groups, n_query, K, device):
         self.n_jobs, self.groups, self.n_query, self.K = n_jobs, groups, n_query, K
@@ -325,43 +355,39 @@ class MaskClipPropagator:
             self._tail(0, len(self.table), want_maps)
         return (self.maps if want_maps else None), self.masks
 
-    def run_host(self, feats_host, onehot_host, masks_host, chunk_frames=8):
+    def run_host(self, feats_host, onehot_host, masks_host, chunks=None):
         """End-to-end form: PINNED host features [T,C,H,W] / one-hot [L,H,W] in, uint8 masks
-        [T,h,w] out to pinned host memory.  The host->device copy of frame chunk i+1 (copy
-        stream) overlaps K0 + K1 + tail of chunk i: a frame's jobs only need earlier frames."""
+        [T,h,w] out to pinned host memory.  The host->device copy of job chunk i+1 (copy stream)
+        overlaps K0 + K1 + tail of chunk i: a frame's jobs only need earlier frames.  ``chunks``:
+        list of (job_begin, job_end); default = :func:`plan_chunks` (full last waves)."""
         cfg = self.cfg
         if not hasattr(self, "_stage"):
             self._stage = torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
             self._onehot = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
             self._copy = torch.cuda.Stream(device=self.device)
-            self._host_chunk = None
-        if self._host_chunk != chunk_frames:
-            # the chunk launches are short: split the memory lists so that their last wave is full
-            self._host_chunk = chunk_frames
-            self._host_groups = pick_groups(min(chunk_frames, max(1, len(self.table))), self.H, self.W,
-                                            self.table.max_mem) if self.T > 1 else 1
-            self._host_lists = TopKLists(max(1, len(self.table)), self._host_groups, self.H * self.W, cfg["topk"],
-                                         self.device)
+            self._chunks = plan_chunks(len(self.table), (-(-self.H // 8)) * (-(-self.W // 16))) if self.T > 1 else []
+        chunks = chunks or self._chunks
         cur = torch.cuda.current_stream()
         self._copy.wait_stream(cur)                       # staging buffers free again
         evs = []
         with torch.cuda.stream(self._copy):
             self._onehot.copy_(onehot_host, non_blocking=True)
-            for s in range(0, self.T, chunk_frames):
-                e = min(self.T, s + chunk_frames)
-                self._stage[s:e].copy_(feats_host[s:e], non_blocking=True)
+            f0 = 0
+            for (j0, j1) in (chunks or [(0, 0)]):
+                f1 = j1 + 1 if j1 > j0 else self.T          # job j propagates frame j + 1
+                self._stage[f0:f1].copy_(feats_host[f0:f1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy)
-                evs.append((s, e, ev))
-        for s, e, ev in evs:
+                evs.append((f0, f1, j0, j1, ev))
+                f0 = f1
+        for f0, f1, j0, j1, ev in evs:
             cur.wait_event(ev)
-            self.bank.load_frames(self._stage[s:e], s, normalize=cfg.get("with_norm", True))
-            if s == 0:
+            self.bank.load_frames(self._stage[f0:f1], f0, normalize=cfg.get("with_norm", True))
+            if f0 == 0:
                 self.labels.put_nchw(self._onehot, 0)
                 self._decode(0)
-            j0, j1 = max(s, 1) - 1, e - 1                 # job t-1 propagates frame t
             if j1 > j0:
-                self._k1(j0, j1, self._host_lists)
-                self._tail(j0, j1, False, self._host_lists)
+                self._k1(j0, j1)
+                self._tail(j0, j1, False)
         masks_host.copy_(self.masks, non_blocking=True)
         return masks_host

@@ -403,7 +403,7 @@ def test_clip_host_pipeline_equals_resident_run():
     want = masks.clone()
     want_maps = maps.clone()
     out = torch.empty(T, 80, 112, dtype=torch.uint8).pin_memory()
-    clip.run_host(feats.pin_memory(), onehot.pin_memory(), out, chunk_frames=3)
+    clip.run_host(feats.pin_memory(), onehot.pin_memory(), out, chunks=[(0, 2), (2, 3), (3, 7), (7, 10)])
     torch.cuda.synchronize()
     assert torch.equal(out, want.cpu())
     # and the label maps agree with the oracle driver loop

@@ -198,3 +198,13 @@ def test_point_sharded_forward_test_world2_gloo(with_first):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_plan_chunks_cover_all_jobs_with_full_waves():
+    for n, tiles in ((63, 56), (49, 128), (5, 56), (1, 56), (249, 128)):
+        ch = engine.plan_chunks(n, tiles)
+        assert ch[0][0] == 0 and ch[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(b > a for a, b in ch)
+    ch = engine.plan_chunks(63, 56)
+    waste = sum(-(-(b - a) * 56 // 148) for a, b in ch) / (63 * 56 / 148)
+    assert waste < 1.15 and (ch[0][1] - ch[0][0]) <= 16 and len(ch) >= 3   # full waves, early start, overlap

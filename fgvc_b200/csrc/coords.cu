@@ -44,31 +44,33 @@ struct GaussSrc {
 
 constexpr int CK = 8;  // candidates kept per thread (>= img2coord topk)
 
-// block-wide soft-argmax over an implicit out_h x out_w map
-template <class Src>
-__device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk, float* out_xy) {
+// (value, index) ordering used by the soft-argmax: larger value first, exact ties -> higher index
+// first (what a stable ascending argsort read from the back gives; np.argsort in img2coord)
+__device__ __forceinline__ bool key_gt(float v, int i, float w, int j) { return v > w || (v == w && i > j); }
+
+// sorted insert under that ordering; independent of the order in which pixels are visited
+template <int K>
+__device__ __forceinline__ void push_key(TopK<K>& t, float x, int i) {
+  if (!key_gt(x, i, t.v[K - 1], t.id[K - 1])) return;
+  bool c[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) c[j] = key_gt(x, i, t.v[j], t.id[j]);
+#pragma unroll
+  for (int j = K - 1; j > 0; --j) {
+    t.v[j] = c[j - 1] ? t.v[j - 1] : (c[j] ? x : t.v[j]);
+    t.id[j] = c[j - 1] ? t.id[j - 1] : (c[j] ? i : t.id[j]);
+  }
+  t.v[0] = c[0] ? x : t.v[0];
+  t.id[0] = c[0] ? i : t.id[0];
+}
+
+// Block-wide selection of the `topk` best (value, index) pairs from the per-thread sorted lists:
+// topk rounds of block arg-max over the list heads.  Results in win_v / win_i (shared).
+__device__ void block_topk(const TopK<CK>& top, int topk, float* win_v, int* win_i) {
   __shared__ float red_v[8];
   __shared__ int red_i[8];
   __shared__ int red_t[8];
-  __shared__ double red_s[8];
-  __shared__ float win_v[CK];
-  __shared__ int win_i[CK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  TopK<CK> top;
-  top.init();
-  double sum = 0.0;
-  const int total = out_h * out_w;
-  for (int o = tid; o < total; o += 256) {
-    int oy = o / out_w, ox = o - oy * out_w;
-    float v = src.at(oy, ox);
-    sum += (double)v;
-    if (v >= top.thr()) top.push_ge(v, o);   // ties: the higher index wins
-  }
-  // all-zero test: np.sum(map) == 0
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) red_s[warp] = sum;
-  // topk rounds of block arg-max over the heads of the per-thread sorted lists
   int head = 0;
   for (int r = 0; r < topk; ++r) {
     float v = -INFINITY;
@@ -82,7 +84,7 @@ __device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk
       float ov = __shfl_xor_sync(0xffffffffu, v, o);
       int oi = __shfl_xor_sync(0xffffffffu, i, o);
       int ot = __shfl_xor_sync(0xffffffffu, t, o);
-      if (ov > v || (ov == v && oi > i)) { v = ov; i = oi; t = ot; }
+      if (key_gt(ov, oi, v, i)) { v = ov; i = oi; t = ot; }
     }
     __syncthreads();
     if (lane == 0) { red_v[warp] = v; red_i[warp] = i; red_t[warp] = t; }
@@ -90,30 +92,147 @@ __device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk
     float bv = red_v[0]; int bi = red_i[0], bt = red_t[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w)
-      if (red_v[w] > bv || (red_v[w] == bv && red_i[w] > bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
+      if (key_gt(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
     if (tid == bt) ++head;
     if (tid == 0) { win_v[r] = bv; win_i[r] = bi; }
   }
   __syncthreads();
+}
+
+// img2coord on the winners (vanilla_tracker.py:181-190): ascending order, fp32 sum + 1e-9, fp32
+// weights, fp64 weighted mean of (idx % w, idx // w); an all-zero map gives -1
+__device__ void write_coords(const float* win_v, const int* win_i, int topk, int out_w, bool nonzero, float* out_xy) {
+  float x = -1.f, y = -1.f;
+  if (nonzero) {
+    float s = 0.f;
+    for (int r = topk - 1; r >= 0; --r) s += win_v[r];
+    s += 1e-9f;
+    double ax = 0.0, ay = 0.0;
+    for (int r = topk - 1; r >= 0; --r) {
+      double w = (double)__fdiv_rn(win_v[r], s);
+      ax += (double)(win_i[r] % out_w) * w;
+      ay += (double)(win_i[r] / out_w) * w;
+    }
+    x = (float)ax; y = (float)ay;
+  }
+  out_xy[0] = x; out_xy[1] = y;
+}
+
+// brute-force soft-argmax over an implicit out_h x out_w map (used for the analytic gaussian)
+template <class Src>
+__device__ void soft_argmax_block(const Src& src, int out_h, int out_w, int topk, float* out_xy) {
+  __shared__ double red_s[8];
+  __shared__ float win_v[CK];
+  __shared__ int win_i[CK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TopK<CK> top;
+  top.init();
+  double sum = 0.0;
+  const int total = out_h * out_w;
+  for (int o = tid; o < total; o += 256) {
+    int oy = o / out_w, ox = o - oy * out_w;
+    float v = src.at(oy, ox);
+    sum += (double)v;
+    push_key(top, v, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red_s[warp] = sum;
+  block_topk(top, topk, win_v, win_i);
   if (tid == 0) {
     double tot = 0.0;
     for (int w = 0; w < 8; ++w) tot += red_s[w];
-    float x = -1.f, y = -1.f;
-    if (tot != 0.0) {
-      // np: ascending order, fp32 sum, + 1e-9, fp32 divide, fp64 weighted mean
-      float s = 0.f;
-      for (int r = topk - 1; r >= 0; --r) s += win_v[r];
-      s += 1e-9f;
-      double ax = 0.0, ay = 0.0;
-      for (int r = topk - 1; r >= 0; --r) {
-        double w = (double)__fdiv_rn(win_v[r], s);
-        ax += (double)(win_i[r] % out_w) * w;
-        ay += (double)(win_i[r] / out_w) * w;
-      }
-      x = (float)ax; y = (float)ay;
-    }
-    out_xy[0] = x; out_xy[1] = y;
+    write_coords(win_v, win_i, topk, out_w, tot != 0.0, out_xy);   // np.sum(map) == 0 -> -1
   }
+}
+
+// first / last output index whose source cell (floor of the clamped source coordinate) is i0
+__device__ __forceinline__ void cell_range(int i0, int in_size, int out_size, float scale, int* lo, int* hi) {
+  // lerp_coord(o).i0 is non-decreasing in o: locate the run of outputs that map to i0 by search
+  // around the analytic estimate (scale = in/out, src = (o + 0.5) * scale - 0.5)
+  int g = (int)floorf(((float)i0 + 0.5f) / scale - 0.5f);
+  g = max(0, min(out_size - 1, g));
+  while (g > 0 && lerp_coord(g - 1, scale, in_size).i0 >= i0) --g;
+  while (g < out_size - 1 && lerp_coord(g, scale, in_size).i0 < i0) ++g;
+  *lo = g;                       // first o with i0(o) >= i0
+  int h = g;
+  while (h < out_size - 1 && lerp_coord(h + 1, scale, in_size).i0 <= i0) ++h;
+  *hi = h;
+}
+
+// Soft-argmax of the bilinearly up-sampled map WITHOUT evaluating every output pixel.  An up-sampled
+// value is a convex combination of its 4 taps, so it cannot exceed their maximum:
+//   1. seed: the 5 largest SOURCE pixels; evaluate the output pixels around them; tau = the topk-th
+//      best up-sampled value found (a lower bound of the final topk-th value);
+//   2. scan the source cells; only cells whose largest tap reaches tau (minus a rounding margin) can
+//      hold a winner -- evaluate just those.
+// Peaked heat-maps touch a handful of cells; a flat map degrades to the full evaluation.  Exact.
+// Zero test: labels are non-negative (convex combinations of gaussians / one-hots), for which
+// "sum of the up-sampled map == 0" <=> "every source value is 0".
+__device__ void soft_argmax_pruned(const float* m, int H, int W, int out_h, int out_w, int topk, float* out_xy) {
+  __shared__ float win_v[CK];
+  __shared__ int win_i[CK];
+  __shared__ int any_nz[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const BilinearSrc src{m, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
+  // ---- 1. seeds
+  TopK<CK> top;
+  top.init();
+  bool nz = false;
+  for (int i = tid; i < H * W; i += 256) {
+    const float v = m[i];
+    nz |= v != 0.f;
+    push_key(top, v, i);
+  }
+  nz = __any_sync(0xffffffffu, nz);
+  if (lane == 0) any_nz[warp] = nz;
+  block_topk(top, topk, win_v, win_i);
+  bool nonzero = false;
+  for (int w = 0; w < 8; ++w) nonzero |= any_nz[w] != 0;
+  // rectangles of output pixels around the seeds (the outputs whose taps include the seed pixel)
+  int ry0[CK], ry1[CK], rx0[CK], rx1[CK];
+  for (int r = 0; r < topk; ++r) {
+    const int sd = win_i[r];
+    if (sd < 0) { ry0[r] = 1; ry1[r] = 0; rx0[r] = 1; rx1[r] = 0; continue; }
+    const int sy = sd / W, sx = sd - sy * W;
+    int t0, t1;
+    cell_range(max(sy - 1, 0), H, out_h, src.sy, &ry0[r], &t0);
+    cell_range(sy, H, out_h, src.sy, &t1, &ry1[r]);
+    cell_range(max(sx - 1, 0), W, out_w, src.sx, &rx0[r], &t0);
+    cell_range(sx, W, out_w, src.sx, &t1, &rx1[r]);
+  }
+  __syncthreads();
+  top.init();
+  for (int r = 0; r < topk; ++r) {
+    const int nx = rx1[r] - rx0[r] + 1, n = max(0, ry1[r] - ry0[r] + 1) * max(0, nx);
+    for (int i = tid; i < n; i += 256) {
+      const int oy = ry0[r] + i / nx, ox = rx0[r] + i % nx;
+      bool seen = false;                        // already covered by an earlier seed's rectangle
+      for (int q = 0; q < r; ++q) seen |= oy >= ry0[q] && oy <= ry1[q] && ox >= rx0[q] && ox <= rx1[q];
+      if (!seen) push_key(top, src.at(oy, ox), oy * out_w + ox);
+    }
+  }
+  block_topk(top, topk, win_v, win_i);
+  // tau = the topk-th best of these (distinct) output pixels: a lower bound of the final topk-th value
+  float tau = (win_i[topk - 1] >= 0) ? win_v[topk - 1] : -INFINITY;
+  __syncthreads();
+  const float tau_safe = tau == -INFINITY ? -INFINITY : tau - fabsf(tau) * 4e-6f - 1e-30f;
+  // ---- 2. cells that can hold a winner
+  top.init();
+  for (int c = tid; c < H * W; c += 256) {
+    const int i0 = c / W, j0 = c - i0 * W;
+    const int i1 = min(i0 + 1, H - 1), j1 = min(j0 + 1, W - 1);
+    const float mx = fmaxf(fmaxf(m[i0 * W + j0], m[i0 * W + j1]), fmaxf(m[i1 * W + j0], m[i1 * W + j1]));
+    if (!(mx >= tau_safe)) continue;
+    int y0, y1, x0, x1;
+    cell_range(i0, H, out_h, src.sy, &y0, &y1);
+    cell_range(j0, W, out_w, src.sx, &x0, &x1);
+    if (lerp_coord(y0, src.sy, H).i0 != i0 || lerp_coord(x0, src.sx, W).i0 != j0) continue;   // cell without outputs
+    for (int oy = y0; oy <= y1; ++oy)
+      for (int ox = x0; ox <= x1; ++ox) push_key(top, src.at(oy, ox), oy * out_w + ox);
+  }
+  block_topk(top, topk, win_v, win_i);
+  if (tid == 0) write_coords(win_v, win_i, topk, out_w, nonzero, out_xy);
 }
 
 __global__ void __launch_bounds__(256)
@@ -126,8 +245,7 @@ heatmap_coords_kernel(const float* __restrict__ maps, int H, int W, int out_h, i
     __syncthreads();
     m = smap;
   }
-  BilinearSrc src{m, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
-  soft_argmax_block(src, out_h, out_w, topk, out_xy + 2 * blockIdx.x);
+  soft_argmax_pruned(m, H, W, out_h, out_w, topk, out_xy + 2 * blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256)
@@ -226,20 +344,6 @@ decode_argmax_kernel(const float* __restrict__ src, int L, int H, int W, int str
 
 // batched form for a clip: blockIdx.y walks jobs [job_begin, job_end); each decodes the label-bank
 // slot jobs[j].out_slot into masks[slot] using minmax[j - job_begin][2L]
-// first / last output index whose source cell (floor of the clamped source coordinate) is i0
-__device__ __forceinline__ void cell_range(int i0, int in_size, int out_size, float scale, int* lo, int* hi) {
-  // lerp_coord(o).i0 is non-decreasing in o: locate the run of outputs that map to i0 by search
-  // around the analytic estimate (scale = in/out, src = (o + 0.5) * scale - 0.5)
-  int g = (int)floorf(((float)i0 + 0.5f) / scale - 0.5f);
-  g = max(0, min(out_size - 1, g));
-  while (g > 0 && lerp_coord(g - 1, scale, in_size).i0 >= i0) --g;
-  while (g < out_size - 1 && lerp_coord(g, scale, in_size).i0 < i0) ++g;
-  *lo = g;                       // first o with i0(o) >= i0
-  int h = g;
-  while (h < out_size - 1 && lerp_coord(h + 1, scale, in_size).i0 <= i0) ++h;
-  *hi = h;
-}
-
 // Per-channel min / max of the up-sampled map.  Within one source cell the bilinear value is
 // monotone along each axis, so its extremes over the output pixels of that cell sit on the four
 // corner-most output pixels: 4 evaluations per cell instead of (out/in)^2.  One thread per source

@@ -474,3 +474,27 @@ def test_raw_c_abi_as_in_integration_md():
     want = fgvc_b200.masked_attention_efficient_v2(feats[T][None], feats[:T].permute(1, 0, 2, 3)[None].contiguous(),
                                                    v, 5, temperature=0.07, topk=K)
     assert torch.equal(got, want)
+
+
+def test_heatmap_coords_pruned_search_is_exact():
+    """K3 evaluates only cells that can hold a top-5 value; compare with the brute-force port on peaked,
+    two-peak, plateau and nearly flat maps at several up-sampling factors (incl. non-integer)."""
+    from fgvc_b200 import engine
+    g = torch.Generator().manual_seed(21)
+    H, W = 24, 31
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    peak = lambda cy, cx, s: torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * s * s))
+    maps = torch.stack([
+        peak(5.3, 7.8, 1.5), peak(0.0, 0.0, 2.0), peak(23.0, 30.0, 1.0),                  # interior / corners
+        0.7 * peak(4.0, 4.0, 1.2) + 0.69 * peak(20.0, 27.0, 1.2),                         # two far peaks
+        torch.full((H, W), 0.25) + 1e-3 * torch.rand(H, W, generator=g),                  # nearly flat
+        (peak(12.0, 15.0, 3.0) > 0.5).float(),                                            # plateau: exact ties
+        torch.rand(H, W, generator=g),
+    ])
+    for out_hw in ((48, 62), (192, 248), (100, 90), (24, 31)):
+        up = torch.nn.functional.interpolate(maps[None], size=out_hw, mode="bilinear", align_corners=False)[0]
+        want = O.img2coord_port(up[None].numpy())[:, :, 0].T
+        got = engine.heatmap_coords(maps.cuda(), out_hw).cpu().numpy()
+        err = np.abs(got - want).max(axis=1)
+        assert (np.delete(err, 5) < 0.02).all(), (out_hw, err)       # smooth maps: same five pixels
+        assert err[5] < 2.0                                          # plateau: ties are broken arbitrarily by numpy

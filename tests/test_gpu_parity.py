@@ -476,9 +476,22 @@ def test_raw_c_abi_as_in_integration_md():
     assert torch.equal(got, want)
 
 
+def _img2coord_high_index_ties(maps, topk=5):
+    """img2coord with a DEFINED tie order (larger value, then larger index), which is what the kernel
+    implements; np.argsort leaves the order of exactly equal values unspecified."""
+    n, h, w = maps.shape
+    out = np.zeros((n, 2))
+    for i in range(n):
+        flat = maps[i].reshape(-1)
+        order = np.lexsort((np.arange(flat.size), flat))[-topk:]
+        v = flat[order] / (flat[order].sum(dtype=np.float32) + np.float32(1e-9))
+        out[i] = [(order % w * v).sum(), (order // w * v).sum()] if flat.sum() != 0 else [-1, -1]
+    return out
+
+
 def test_heatmap_coords_pruned_search_is_exact():
-    """K3 evaluates only cells that can hold a top-5 value; compare with the brute-force port on peaked,
-    two-peak, plateau and nearly flat maps at several up-sampling factors (incl. non-integer)."""
+    """K3 evaluates only cells that can hold a top-5 value; compare with brute force on peaked, corner,
+    two-peak, plateau (exact ties) and nearly flat maps at several up-sampling factors."""
     from fgvc_b200 import engine
     g = torch.Generator().manual_seed(21)
     H, W = 24, 31
@@ -486,15 +499,16 @@ def test_heatmap_coords_pruned_search_is_exact():
     peak = lambda cy, cx, s: torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * s * s))
     maps = torch.stack([
         peak(5.3, 7.8, 1.5), peak(0.0, 0.0, 2.0), peak(23.0, 30.0, 1.0),                  # interior / corners
-        0.7 * peak(4.0, 4.0, 1.2) + 0.69 * peak(20.0, 27.0, 1.2),                         # two far peaks
+        0.7 * peak(4.2, 4.6, 1.2) + 0.69 * peak(20.4, 27.7, 1.2),                         # two far peaks
         torch.full((H, W), 0.25) + 1e-3 * torch.rand(H, W, generator=g),                  # nearly flat
         (peak(12.0, 15.0, 3.0) > 0.5).float(),                                            # plateau: exact ties
         torch.rand(H, W, generator=g),
     ])
     for out_hw in ((48, 62), (192, 248), (100, 90), (24, 31)):
         up = torch.nn.functional.interpolate(maps[None], size=out_hw, mode="bilinear", align_corners=False)[0]
-        want = O.img2coord_port(up[None].numpy())[:, :, 0].T
+        want = _img2coord_high_index_ties(up.numpy())
         got = engine.heatmap_coords(maps.cuda(), out_hw).cpu().numpy()
         err = np.abs(got - want).max(axis=1)
-        assert (np.delete(err, 5) < 0.02).all(), (out_hw, err)       # smooth maps: same five pixels
-        assert err[5] < 2.0                                          # plateau: ties are broken arbitrarily by numpy
+        assert (err < 0.02).all(), (out_hw, err)
+        ref = O.img2coord_port(up[None].numpy())[:, :, 0].T          # the reference's own (tie order unspecified)
+        assert np.abs(got - ref)[[0, 3, 6]].max() < 0.02      # maps without (near-)ties

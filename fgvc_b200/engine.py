@@ -177,6 +177,29 @@ def plan_chunks(n_jobs, tiles, copy_ratio=0.75, launch_cost=0.4):
     return cuts
 
 
+def plan_overlap_chunks(n_jobs, tiles, max_chunks=6):
+    """Split the jobs of a resident clip into the largest number of K1 launches (<= max_chunks) that
+    costs no extra round compared with one launch, so that the gather chain of chunk i (second stream)
+    can overlap K1 of chunk i+1 for free.  Falls back to a single launch."""
+    def rounds(n):
+        return -(-n * tiles // NUM_SMS)
+
+    single = rounds(n_jobs)
+    best = [(0, n_jobs)]
+    for k in range(2, max_chunks + 1):
+        if k > n_jobs:
+            break
+        base, extra = divmod(n_jobs, k)
+        sizes = [base + (1 if i < extra else 0) for i in range(k)]
+        if sum(rounds(n) for n in sizes) <= single:
+            cuts, s0 = [], 0
+            for n in sizes:
+                cuts.append((s0, s0 + n))
+                s0 += n
+            best = cuts
+    return best
+
+
 class TopKLists:
     def __init__(self, n_jobs, groups, n_query, K, device):
         self.n_jobs, self.groups, self.n_query, self.K = n_jobs, groups, n_query, K
@@ -313,6 +336,8 @@ class MaskClipPropagator:
         self.masks = torch.empty(T, out_hw[0], out_hw[1], dtype=torch.uint8, device=device)
         self.scratch = torch.empty(max(T, 1) * 2 * L, dtype=torch.float32, device=device)
         self.k1_events = None
+        self._tail_stream = None
+        self._overlap = plan_overlap_chunks(len(self.table), (-(-H // 8)) * (-(-W // 16))) if T > 1 else []
         self.temperature, self.flags = sim_params(cfg, C, cfg["temperature"], sim_mode=cfg.get("sim_mode", "dot_product"),
                                                   normalize=cfg.get("with_norm", True))
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
@@ -348,11 +373,31 @@ class MaskClipPropagator:
             if events:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self._k1(0, len(self.table))
+            if len(self._overlap) <= 1:
+                self._k1(0, len(self.table))
+                if events:
+                    e1.record()
+                self._tail(0, len(self.table), want_maps)
+            else:
+                # K1 in a few launches on this stream; the sequential gather chain + decode of chunk i run
+                # on a high-priority side stream while K1 of chunk i+1 keeps the SMs busy
+                if self._tail_stream is None:
+                    self._tail_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                cur = torch.cuda.current_stream()
+                side = self._tail_stream
+                side.wait_stream(cur)                      # label bank slot 0 / previous use of the buffers
+                for (j0, j1) in self._overlap:
+                    self._k1(j0, j1)
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    with torch.cuda.stream(side):
+                        side.wait_event(ev)
+                        self._tail(j0, j1, want_maps)
+                if events:
+                    e1.record()
+                cur.wait_stream(side)
             if events:
-                e1.record()
                 self.k1_events = (e0, e1)
-            self._tail(0, len(self.table), want_maps)
         return (self.maps if want_maps else None), self.masks
 
     def run_host(self, feats_host, onehot_host, masks_host, chunks=None):

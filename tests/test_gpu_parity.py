@@ -228,6 +228,28 @@ def test_properties_at_full_size(engine):
     assert torch.equal(same, lab[:, :, 0])
 
 
+@pytest.mark.parametrize("engine", ["tc16", "tc"])
+def test_properties_at_point_tracking_size(engine):
+    """BASELINE config 3/5 geometry (128x128, r=15, T=6 with frame 0 twice, k=10): weights sum to one,
+    linearity, and agreement of the tensor engines with the CUDA-core engine on tie-free queries."""
+    import fgvc_b200
+    g = torch.Generator().manual_seed(31)
+    H = W = 128
+    C, L = 256, 8
+    f = _coherent(g, 6, C, H, W).cuda()
+    k = f[[0, 0, 1, 2, 3, 4]].permute(1, 0, 2, 3)[None].contiguous()
+    q = f[5][None]
+    ones = torch.ones(1, L, 6, H, W, device="cuda")
+    out = fgvc_b200.masked_attention_efficient_v2(q, k, ones, 15, temperature=0.07, topk=10, **_eng(engine))
+    assert (out - 1).abs().max() < 1e-5
+    v = torch.rand(1, L, 6, H, W, generator=g).cuda()
+    a = fgvc_b200.masked_attention_efficient_v2(q, k, v, 15, temperature=0.07, topk=10, **_eng(engine))
+    b = fgvc_b200.masked_attention_efficient_v2(q, k, v, 15, temperature=0.07, topk=10, **_eng("simt"))
+    diff = (a - b).abs().amax(dim=1).flatten()
+    assert float((diff > TOL).float().mean()) <= 1e-3          # >= 99.9 % of the queries within 1e-3
+    assert float(diff.median()) < 1e-6
+
+
 # ---------------------------------------------------------------------------- K0 / K3
 def test_prep_features_matches_normalize():
     from fgvc_b200.engine import FeatureBank

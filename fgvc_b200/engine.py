@@ -337,7 +337,10 @@ class MaskClipPropagator:
         self.scratch = torch.empty(max(T, 1) * 2 * L, dtype=torch.float32, device=device)
         self.k1_events = None
         self._tail_stream = None
-        self._overlap = plan_overlap_chunks(len(self.table), (-(-H // 8)) * (-(-W // 16))) if T > 1 else []
+        # optional: K1 in a few launches with the gather chain of chunk i on a side stream under K1 of chunk
+        # i+1.  Measured on config 2 it does not pay (the tail is real SM work, not latency): off by default.
+        self._overlap = (plan_overlap_chunks(len(self.table), (-(-H // 8)) * (-(-W // 16)))
+                         if (T > 1 and cfg.get("overlap_tail", False)) else [])
         self.temperature, self.flags = sim_params(cfg, C, cfg["temperature"], sim_mode=cfg.get("sim_mode", "dot_product"),
                                                   normalize=cfg.get("with_norm", True))
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()

@@ -73,9 +73,14 @@ static int affinity_topk_impl(const void* feat_bank, int32_t fmt, int32_t n_slot
   int rc = pick_engine(engine, fmt, H, W, C, K, &use_tc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc && fmt == FGVC_BANK_F16)
-    return launch_affinity_topk_tc16(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
-                                     groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
+  if (use_tc && fmt == FGVC_BANK_F16) {
+    rc = launch_affinity_topk_tc16(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                                   groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
+    if (rc != FGVC_ERR_UNSUPPORTED || engine != FGVC_ENGINE_AUTO) return rc;
+    // a shape the tensor kernel does not take (e.g. a huge map with unmasked frames): CUDA-core engine
+    return launch_affinity_topk_simt(feat_bank, fmt, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                                     groups, topk_val, topk_idx, st);
+  }
   if (use_tc)
     return launch_affinity_topk_tc(reinterpret_cast<const float*>(feat_bank), n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
                                    groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);

@@ -30,7 +30,7 @@ constexpr int T16_MAX_BH = 4;                  // N <= 64, 2N <= 128 accumulator
 constexpr int T16_AHI_COL = 256, T16_ALO_COL = 384;
 constexpr int T16_EPI_WG = 4;
 constexpr int T16_THREADS = 64 + 128 * T16_EPI_WG;
-constexpr int T16_MAX_BOXES = 1024;             // per box list (masked halo / whole frame)
+constexpr int T16_MAX_BOXES = 4096;             // per box list (masked halo / whole frame)
 constexpr int T16_AUX_BYTES = 1024 + 2 * T16_MAX_BOXES * 4;
 constexpr int T16_SMEM_BYTES = T16_STAGES * T16_STAGE_BYTES + T16_AUX_BYTES;
 
@@ -471,8 +471,10 @@ int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C
   static const int exp_flags = getenv("FGVC_TC16_EXP") ? atoi(getenv("FGVC_TC16_EXP")) : 0;   // perf experiments only
   p.exp_flags = exp_flags;
   FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 f16 engine: radius %d too large", radius);
-  FGVC_CHECK_ARG(cdiv(H, p.BH) * cdiv(W, 16) <= T16_MAX_BOXES && H < 65536 && W < 65536,
-                 "tcgen05 f16 engine: %dx%d map has too many key boxes", H, W);
+  if (cdiv(H, p.BH) * cdiv(W, 16) > T16_MAX_BOXES || H >= 65536 || W >= 65536) {
+    set_error("tcgen05 f16 engine: a %dx%d map has more than %d key boxes", H, W, T16_MAX_BOXES);
+    return FGVC_ERR_UNSUPPORTED;      // AUTO falls back to the CUDA-core engine
+  }
   CUtensorMap mk;
   int rc = make_map16(&mk, bank, n_slots, H, W, C, p.BH);
   if (rc) return rc;

@@ -139,6 +139,25 @@ def gen_tracker():
     np.savez_compressed(os.path.join(OUT, "tracker.npz"), **out)
 
 
+def gen_tapvid_metrics():
+    fn = ref_loader.load_tapvid_metrics()
+    rs = np.random.RandomState(5)
+    b, n, T = 2, 9, 12
+    qp = np.stack([rs.randint(0, 5, (b, n)).astype(np.float64), rs.rand(b, n) * 256, rs.rand(b, n) * 256], -1)
+    gt_occ = rs.rand(b, n, T) < 0.25
+    for i in range(b):
+        for j in range(n):
+            gt_occ[i, j, int(qp[i, j, 0])] = False
+    gt = rs.rand(b, n, T, 2) * 256
+    pred = gt + rs.randn(b, n, T, 2) * rs.choice([0.5, 3.0, 12.0], (b, n, T, 1))
+    pred_occ = gt_occ ^ (rs.rand(b, n, T) < 0.2)
+    d = dict(qp=qp, gt_occ=gt_occ, gt=gt, pred_occ=pred_occ, pred=pred)
+    for mode in ("first", "strided"):
+        for k, v in fn(qp, gt_occ, gt, pred_occ, pred, mode).items():
+            d[f"{mode}__{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "tapvid_metrics.npz"), **d)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
@@ -149,6 +168,7 @@ def main():
     gen_c2f(ref)
     gen_legacy(ref)
     gen_tracker()
+    gen_tapvid_metrics()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -363,6 +363,41 @@ def propagate_legacy_port(img, affinity, topk=None):
     return torch.bmm(img.reshape(B, L, -1), aff).reshape(B, L, H, W)
 
 
+# -------------------------------------------------------------------------- TAP-Vid metrics
+def tapvid_metrics_port(query_points, gt_occluded, gt_tracks, pred_occluded, pred_tracks, query_mode="first"):
+    """numpy restatement of ``compute_tapvid_metrics`` (tapvid_evaluation_datasets.py:106-249):
+    query_points [b,n,3] (t,y,x); *_occluded bool [b,n,T]; *_tracks [b,n,T,2] (x,y).  The query frame
+    (and, for 'first', everything before the first visible frame) is not evaluated; occlusion accuracy
+    divides by the evaluated points of the WHOLE batch, as the reference does."""
+    T = gt_tracks.shape[2]
+    qf = np.round(query_points[..., 0]).astype(np.int32)
+    ev = np.eye(T)[qf] == 0
+    if query_mode == "first":
+        for i in range(gt_occluded.shape[0]):
+            first = np.where(gt_occluded[i] == 0)[0][0]
+            ev[i, :first] = False
+    elif query_mode != "strided":
+        raise ValueError("Unknown query mode " + query_mode)
+    out = {"occlusion_accuracy": ((pred_occluded == gt_occluded) & ev).sum((1, 2)) / ev.sum()}
+    vis, pvis = ~gt_occluded, ~pred_occluded
+    d2 = ((pred_tracks - gt_tracks) ** 2).sum(-1)
+    fr, ja = [], []
+    for th in (1, 2, 4, 8, 16):
+        within = d2 < th * th
+        correct = within & vis
+        n_vis = (vis & ev).sum((1, 2))
+        f = (correct & ev).sum((1, 2)) / n_vis
+        tp = (correct & pvis & ev).sum((1, 2))
+        fp = ((((~vis) & pvis) | ((~within) & pvis)) & ev).sum((1, 2))
+        j = tp / (n_vis + fp)
+        out[f"pts_within_{th}"], out[f"jaccard_{th}"] = f, j
+        fr.append(f)
+        ja.append(j)
+    out["average_jaccard"] = np.stack(ja, 1).mean(1)
+    out["average_pts_within_thresh"] = np.stack(fr, 1).mean(1)
+    return out
+
+
 # ------------------------------------------------------------------- comparison helper
 def compare_labels(got, exact, gap=None, tol=1e-3, gap_eps=2e-4):
     """Parity report used by the GPU tests.  ``got``/``exact`` [L,H,W]; ``gap`` [Nq] from

@@ -269,3 +269,18 @@ def load_tracker():
     _TRACKER = types.SimpleNamespace(VanillaTracker=vt.VanillaTracker, ResNet=rn.ResNet,
                                      TestCfg=TestCfg, module=vt)
     return _TRACKER
+
+
+def load_tapvid_metrics():
+    """Genuine ``compute_tapvid_metrics`` (mmpt/datasets/tapvid_evaluation_datasets.py:106-249).  The
+    module imports tensorflow-era dependencies at the top, so only the function definition is taken
+    from the file (by ast) and executed with numpy in scope; nothing is copied into the repo."""
+    import ast
+    from typing import Iterable, Mapping
+    import numpy as np
+    path = os.path.join(REF_ROOT, "mmpt/datasets/tapvid_evaluation_datasets.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "compute_tapvid_metrics"][0]
+    ns = dict(np=np, Iterable=Iterable, Mapping=Mapping)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["compute_tapvid_metrics"]

@@ -133,3 +133,17 @@ def test_live_reference_agrees_with_port():
     want = ref.masked_attention_efficient(q, k, v, m, temperature=0.07, topk=10, step=50)
     got = O.propagate_port(q, k, v, mask=O.neighbor_mask(11, 13, 8), temperature=0.07, topk=10, step=50)
     assert torch.allclose(got, want, atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("mode", ["first", "strided"])
+def test_tapvid_metrics_match_reference(golden_dir, mode):
+    d = _load(golden_dir, "tapvid_metrics.npz")
+    got = O.tapvid_metrics_port(d["qp"], d["gt_occ"], d["gt"], d["pred_occ"], d["pred"], mode)
+    from fgvc_b200 import metrics
+    dev = metrics.compute_tapvid_metrics(*(torch.from_numpy(d[k]) for k in ("qp", "gt_occ", "gt", "pred_occ", "pred")),
+                                         query_mode=mode)
+    keys = [k[len(mode) + 2:] for k in d.files if k.startswith(mode + "__")]
+    assert len(keys) == 13
+    for k in keys:
+        assert np.allclose(got[k], d[f"{mode}__{k}"], atol=1e-12), k
+        assert np.allclose(dev[k].numpy(), d[f"{mode}__{k}"], atol=1e-12), k

@@ -346,7 +346,7 @@ def main():
             args.steps = 3
         return run_reference(args)
     if args.steps is None:
-        args.steps = 30
+        args.steps = 20
     run_ours(args)
 
 

@@ -413,10 +413,12 @@ class MaskClipPropagator:
             self._stage = torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
             self._onehot = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
             self._copy = torch.cuda.Stream(device=self.device)
+            self._back = torch.cuda.Stream(device=self.device)      # device->host copies of finished masks
             self._chunks = plan_chunks(len(self.table), (-(-self.H // 8)) * (-(-self.W // 16))) if self.T > 1 else []
         chunks = chunks or self._chunks
         cur = torch.cuda.current_stream()
         self._copy.wait_stream(cur)                       # staging buffers free again
+        self._back.wait_stream(cur)
         evs = []
         with torch.cuda.stream(self._copy):
             self._onehot.copy_(onehot_host, non_blocking=True)
@@ -437,5 +439,12 @@ class MaskClipPropagator:
             if j1 > j0:
                 self._k1(j0, j1)
                 self._tail(j0, j1, False)
-        masks_host.copy_(self.masks, non_blocking=True)
+            # ship the masks of this chunk while the next chunk computes (PCIe is full duplex)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(self._back):
+                self._back.wait_event(done)
+                m0 = 0 if f0 == 0 else f0
+                masks_host[m0:f1].copy_(self.masks[m0:f1], non_blocking=True)
+        cur.wait_stream(self._back)
         return masks_host

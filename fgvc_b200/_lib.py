@@ -14,7 +14,7 @@ MASK_CIRCLE, MASK_SQUARE = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 BANK_TF32, BANK_F16 = 0, 1
 MEM_UNMASKED = 0x40000000
-WEIGHT_COSINE, SIM_L2 = 1, 2
+WEIGHT_COSINE, SIM_L2, HARD_PROP = 1, 2, 4
 
 
 class FgvcError(RuntimeError):

@@ -17,7 +17,28 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
   FGVC_CHECK_ARG(L > 0 && L <= 255 && Lp >= L && Lp % 4 == 0, "fgvc_mask_clip_tail: bad label sizes");
   const int n_pix = H * W;
   const int64_t mask_elems = (int64_t)out_h * out_w;
-  (void)mask_elems;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & FGVC_HARD_PROP) {
+    // hard propagation: the memory keeps one_hot(argmax) of every propagated frame, the prediction is
+    // decoded from the soft labels first (vanilla_tracker.py:762-798) -- so decode per frame
+    for (int j = job_begin; j < job_end; ++j) {
+      int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
+                                  temperature, flags, lab_bank, Lp, stream);
+      if (rc) return rc;
+      const int slot = jobs_host[j].out_slot;
+      float* lab_slot = lab_bank + (int64_t)slot * n_pix * Lp;
+      if (maps_nchw) {
+        rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
+        if (rc) return rc;
+      }
+      rc = launch_decode(lab_slot, true, L, Lp, H, W, out_h, out_w, reinterpret_cast<uint32_t*>(scratch_minmax),
+                         masks + slot * mask_elems, st);
+      if (rc) return rc;
+      rc = launch_labels_harden(lab_slot, n_pix, L, Lp, st);
+      if (rc) return rc;
+    }
+    return FGVC_OK;
+  }
   // the recurrence lives only in the gather: run the chain first ...
   for (int j = job_begin; j < job_end; ++j) {
     int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
@@ -31,7 +52,7 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
   }
   // ... then decode every frame of the range in two batched launches (scratch: [n_jobs][2L] words)
   return launch_decode_jobs(lab_bank, jobs_dev, job_begin, job_end, L, Lp, H, W, out_h, out_w,
-                            reinterpret_cast<uint32_t*>(scratch_minmax), masks, (cudaStream_t)stream);
+                            reinterpret_cast<uint32_t*>(scratch_minmax), masks, st);
 }
 
 // Point tracking tail: the gather chain over jobs [job_begin, job_end) with an NCHW copy of every

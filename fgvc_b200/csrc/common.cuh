@@ -153,6 +153,7 @@ int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C
                               float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st);
 int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
                        int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st);
+int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st);
 int launch_decode(const float* src, bool pixmajor, int L, int Lp, int H, int W, int out_h, int out_w,
                   uint32_t* minmax, uint8_t* out, cudaStream_t st);
 

@@ -114,6 +114,27 @@ gaussian_labels_kernel(const float* __restrict__ pts, int P, int H, int W, int s
   dst[i] = v;
 }
 
+// hard propagation (vanilla_tracker.py:762-767): replace the soft labels of a slot by one_hot(argmax)
+__global__ void __launch_bounds__(256)
+labels_harden_kernel(float* __restrict__ lab, int n_pix, int L, int Lp) {
+  int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n_pix) return;
+  float* row = lab + (int64_t)p * Lp;
+  float best = row[0];
+  int arg = 0;
+  for (int l = 1; l < L; ++l) {
+    float v = row[l];
+    if (v > best) { best = v; arg = l; }     // first maximum, like torch.argmax
+  }
+  for (int l = 0; l < Lp; ++l) row[l] = (l == arg) ? 1.f : 0.f;
+}
+
+int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st) {
+  labels_harden_kernel<<<cdiv(n_pix, 256), 256, 0, st>>>(lab_slot, n_pix, L, Lp);
+  FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
 }  // namespace fgvc
 
 using namespace fgvc;

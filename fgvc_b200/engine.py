@@ -343,6 +343,8 @@ class MaskClipPropagator:
                          if (T > 1 and cfg.get("overlap_tail", False)) else [])
         self.temperature, self.flags = sim_params(cfg, C, cfg["temperature"], sim_mode=cfg.get("sim_mode", "dot_product"),
                                                   normalize=cfg.get("with_norm", True))
+        if cfg.get("hard_prop", False):
+            self.flags |= _lib.HARD_PROP
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 
     def _decode(self, t):

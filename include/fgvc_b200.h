@@ -81,6 +81,8 @@ typedef struct fgvc_job {
 
 /* fgvc_gather_labels flags */
 #define FGVC_WEIGHT_COSINE 1 /* weights = clamp(a, 0)^2 instead of softmax(a)   (mode='cosine', local_attention.py:371) */
+#define FGVC_HARD_PROP 4     /* clip tails only: the memory keeps one_hot(argmax) of each propagated frame
+                                (hard_prop, vanilla_tracker.py:762-767); predictions still decode the soft labels */
 #define FGVC_SIM_L2 2        /* a = (2 cos - 1) / temperature with temperature := sqrt(C)
                                 (sim_mode='l2-distance' on normalised features, local_attention.py:324-327) */
 

@@ -411,6 +411,35 @@ def test_mask_propagation_argmax_agreement():
         assert agree >= 0.999, (t, agree)
 
 
+def test_hard_propagation_keeps_onehot_memory():
+    """hard_prop (vanilla_tracker.py:762-767): the memory stores one_hot(argmax) of each propagated frame,
+    predictions still come from the soft labels.  Oracle loop = port + argmax/one_hot."""
+    from fgvc_b200 import engine
+    g = torch.Generator().manual_seed(21)
+    T, C, H, W, L = 7, 64, 24, 30, 5
+    feats = _coherent(g, T, C, H, W)
+    seg = (torch.arange(H).view(-1, 1) // 9 + (torch.arange(W).view(1, -1) // 16) * 3).clamp(max=L - 1)
+    onehot = torch.nn.functional.one_hot(seg, L).permute(2, 0, 1).float().contiguous()
+    cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=10, with_first=True,
+               with_first_neighbor=True, hard_prop=True)
+    clip = engine.MaskClipPropagator(T, C, H, W, L, (96, 120), cfg, torch.device("cuda"))
+    maps, masks = clip.run(feats.cuda(), onehot.cuda(), want_maps=True)
+    bank, mask = [onehot], O.neighbor_mask(H, W, 10)
+    bad = tot = 0
+    for t in range(1, T):
+        mem = O.memory_frames(t, 3)
+        kk = feats[mem].permute(1, 0, 2, 3)[None]
+        vv = torch.stack([bank[m] for m in mem], dim=1)[None]
+        soft = O.propagate_port(feats[t][None], kk, vv, mask=mask, temperature=0.07, topk=10)[0]
+        bank.append(torch.nn.functional.one_hot(soft.argmax(0), L).permute(2, 0, 1).float())
+        err = (maps[t].cpu() - soft).abs().amax(0)
+        bad += int((err > TOL).sum()); tot += err.numel()
+        want = O.decode_masks_port(soft, (96, 120))
+        assert float((masks[t].cpu().long() == want).float().mean()) >= 0.995, t
+    # an argmax flip on a near-tie changes one memory pixel for later frames; it must stay rare
+    assert bad / tot <= 5e-3, bad / tot
+
+
 def test_clip_host_pipeline_equals_resident_run():
     """The end-to-end path (pinned host buffers, chunked copies overlapping K0/K1/tail per
     chunk) must give bit-identical masks to the one-launch resident path."""

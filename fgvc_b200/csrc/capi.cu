@@ -96,6 +96,41 @@ extern "C" int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, in
                             K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
 }
 
+extern "C" int64_t fgvc_affinity_topk_workspace_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K) {
+  return tc16p_workspace_bytes(n_jobs, groups, n_query, K);
+}
+
+extern "C" int fgvc_prefilter_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K, int32_t groups) {
+  return (bank_format == FGVC_BANK_F16 && tc16p_supported(H, W, C, K, groups)) ? 1 : 0;
+}
+
+extern "C" int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,
+                                     int32_t C, const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                                     int32_t radius, int32_t mask_mode, int32_t K, int32_t groups, float* topk_val,
+                                     int32_t* topk_idx, int32_t engine, int32_t unit_rows, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  const bool can = bank_format == FGVC_BANK_F16 && unit_rows != 0 && K >= 1 && K <= 16 &&
+                   tc16p_supported(H, W, C, K, groups);
+  if (engine == FGVC_ENGINE_PREFILTER)
+    FGVC_CHECK_ARG(can, "prefilter engine needs an F16 bank of unit rows, C %% 64 == 0, C <= 256, K <= 16, groups <= 8 "
+                        "(format=%d unit_rows=%d C=%d K=%d groups=%d)", bank_format, unit_rows, C, K, groups);
+  const bool use = engine == FGVC_ENGINE_PREFILTER ||
+                   (engine == FGVC_ENGINE_AUTO && can && workspace != nullptr &&
+                    workspace_bytes >= tc16p_workspace_bytes(n_jobs, groups, H * W, K));
+  if (!use)
+    return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
+                              K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
+  FGVC_CHECK_ARG(feat_bank && jobs && mem_feat_slot && topk_val && topk_idx, "fgvc_affinity_topk_ws: null pointer");
+  FGVC_CHECK_ARG(H > 0 && W > 0 && n_jobs > 0 && n_slots > 0, "fgvc_affinity_topk_ws: bad shape");
+  FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk_ws: radius=%d must be >= 1", radius);
+  FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk_ws: bad mask mode");
+  int rc = launch_affinity_topk_tc16p(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
+                                      groups, topk_val, topk_idx, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (rc != FGVC_ERR_UNSUPPORTED || engine != FGVC_ENGINE_AUTO) return rc;
+  return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
+                            K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
+}
+
 extern "C" int fgvc_debug_affinity_boxes(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                                          const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                                          int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,

@@ -46,6 +46,10 @@ __host__ __device__ inline int64_t feat_slot_floats(int n_pix, int C) { return 2
 // x = hi + lo * 2^-11 for the fp16 split (hi = fp16(x), lo = fp16((x - hi) * 2^11))
 #define FGVC_F16_LO_SCALE 2048.0f
 #define FGVC_F16_LO_INV (1.0f / 2048.0f)
+// |<hi_q, hi_k> - <q, k>| for unit rows: <= 2^-10 from the two fp16 roundings (Cauchy-Schwarz) plus
+// < 6e-5 of fp32 accumulation over C <= 256 products; the prefilter engine (topk_tc16p.cu) uses this
+// bound with margin
+#define FGVC_PREFILTER_EPS 1.25e-3f
 
 // 4 consecutive channels of pixel `pix` of slot `slot`, reconstructed to fp32, for either bank format
 template <int FMT>
@@ -151,6 +155,11 @@ bool tc16_supported(int H, int W, int C, int K);
 int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
                               float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st);
+bool tc16p_supported(int H, int W, int C, int K, int groups);
+int64_t tc16p_workspace_bytes(int n_jobs, int groups, int n_pix, int K);
+int launch_affinity_topk_tc16p(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
+                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv,
+                               int32_t* ti, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
                        int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st);
 int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st);

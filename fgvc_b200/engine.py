@@ -40,6 +40,7 @@ class FeatureBank:
         self.fmt = _lib.BANK_F16 if self.split == "f16" else _lib.BANK_TF32
         dt = torch.float16 if self.split == "f16" else torch.float32
         self.buf = torch.empty(n_slots, 2, H * W, C, dtype=dt, device=device)
+        self.unit_rows = True          # until a frame is loaded without normalisation (prefilter engine needs it)
 
     def dense(self):
         """fp32 [slot, H*W, C] view of what the split encodes (tests / diagnostics)."""
@@ -52,6 +53,8 @@ class FeatureBank:
         ``src.data_ptr + 4*(f*frame_stride + c*chan_stride + p)``."""
         assert src.is_cuda and src.dtype == torch.float32
         assert 0 <= first_slot and first_slot + n_frames <= self.n_slots
+        if not normalize:
+            self.unit_rows = False
         call("fgvc_prep_features", ptr(src), frame_stride, chan_stride, n_frames, self.C, self.H, self.W,
              int(bool(normalize)), ptr(self.buf), self.fmt, first_slot, stream_ptr())
 
@@ -207,9 +210,25 @@ class TopKLists:
         self.idx = torch.empty(n_jobs, groups, n_query, K, dtype=torch.int32, device=device)
 
 
+_WORKSPACES = {}
+
+
+def _workspace(dev, nbytes):
+    """Caller-owned scratch of the prefilter engine, one per (device, stream), grown on demand.  Work on
+    one stream is ordered, so consecutive K1 launches can share it."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
                   job_range=None):
-    """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch."""
+    """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch.  ``AUTO``
+    = the prefilter engine (one fp16 tensor MAC per pair + exact rescoring) for F16 banks of unit rows, else
+    the exact tensor engine of the bank format, else the CUDA-core engine."""
     dev = bank.buf.device
     jobs, mem_feat, _ = table.device(dev)
     if groups is None:
@@ -220,10 +239,15 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
-    call("fgvc_affinity_topk", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
+    ws, ws_bytes = None, 0
+    if engine in (_lib.ENGINE_AUTO, _lib.ENGINE_PREFILTER) and bank.unit_rows and \
+            _lib.load().fgvc_prefilter_supported(bank.fmt, bank.H, bank.W, bank.C, int(K), int(groups)):
+        ws_bytes = int(_lib.load().fgvc_affinity_topk_workspace_bytes(j1 - j0, int(groups), lists.n_query, int(K)))
+        ws = _workspace(dev, ws_bytes)
+    call("fgvc_affinity_topk_ws", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
          ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
          ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),
-         int(engine), stream_ptr())
+         int(engine), int(bool(bank.unit_rows)), ptr(ws) if ws is not None else None, ws_bytes, stream_ptr())
     return lists
 
 

@@ -68,7 +68,17 @@ typedef enum fgvc_mask_mode { FGVC_MASK_CIRCLE = 0, FGVC_MASK_SQUARE = 1 } fgvc_
 /* affinity engines of K1.  AUTO picks the tcgen05 kernel matching the bank format whenever the
  * shape allows (TF32 bank: C % 32 == 0; F16 bank: C % 64 == 0; K <= 16); SIMT is the fp32
  * CUDA-core kernel for every other shape. */
-typedef enum fgvc_engine { FGVC_ENGINE_AUTO = 0, FGVC_ENGINE_SIMT = 1, FGVC_ENGINE_TCGEN05 = 2 } fgvc_engine;
+typedef enum fgvc_engine {
+  FGVC_ENGINE_AUTO = 0,
+  FGVC_ENGINE_SIMT = 1,
+  FGVC_ENGINE_TCGEN05 = 2,
+  /* F16 bank with UNIT rows (K0 with normalize = 1) only: one fp16 tensor MAC per (query, key) pair finds a
+   * rigorous superset of the top-K (|error| <= 1.25e-3 => band of 2.5e-3 below the K-th value), the superset is
+   * re-scored exactly in fp32 and the exact top-K is taken from it; queries whose superset may be
+   * incomplete are re-done by an exact scan.  Same results as TCGEN05 at a third of the tensor work.
+   * Needs the workspace of fgvc_affinity_topk_ws. */
+  FGVC_ENGINE_PREFILTER = 3
+} fgvc_engine;
 
 /* One propagation job = one query frame and its memory list (a multiset of frames:
  * frame 0 appears twice while t <= precede_frames, vanilla_tracker.py:346-362). */
@@ -131,6 +141,18 @@ FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int3
                        const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
+
+/* Same with a caller-owned workspace: needed by FGVC_ENGINE_PREFILTER (candidate lists + the queue of
+ * queries for the exact scan); with a workspace AUTO prefers the prefilter engine when
+ * `unit_rows` != 0 (every bank slot used was written by K0 with normalize = 1), the bank is F16 and
+ * the shape allows (C % 64 == 0, C <= 256, groups <= 8).  fgvc_affinity_topk_workspace_bytes gives the size. */
+FGVC_API int64_t fgvc_affinity_topk_workspace_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K);
+FGVC_API int fgvc_prefilter_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K, int32_t groups);
+FGVC_API int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,
+                       int32_t C, const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
+                       float* topk_val, int32_t* topk_idx, int32_t engine, int32_t unit_rows,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* test hook (tcgen05 engine, groups = 1, use with ONE query tile): additionally dumps the
  * raw 128 x 128 accumulator tile of the first dbg_max_boxes key boxes to

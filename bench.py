@@ -160,8 +160,9 @@ def run_ours(args):
     feats, onehot = build_inputs(dev, seed=1000 + rank)
     T = WORK["clip_frames"]
     H, W = WORK["feat_hw"]
+    eng = {"auto": _lib.ENGINE_AUTO, "prefilter": _lib.ENGINE_PREFILTER}[args.engine]
     clip = engine.MaskClipPropagator(T, WORK["channels"], H, W, WORK["objects"], WORK["image_hw"], CFG, dev,
-                                     split=args.split)
+                                     engine_id=eng, split=args.split)
     split = clip.bank.split
     gathered = torch.empty((world,) + tuple(clip.masks.shape), dtype=torch.uint8, device=dev) if world > 1 else None
 
@@ -238,6 +239,8 @@ def run_ours(args):
         peak = pk["bf16"] / 3.0 if split == "f16" else pk["bf16"] / 2.0 / 3.0
         kname = "affinity_topk_tc16_kernel (K1, fp16 three-term split)" if split == "f16" else \
             "affinity_topk_tc_kernel (K1, 3xTF32)"
+        if args.engine == "prefilter":
+            kname = "affinity_prefilter_tc16_kernel + rescore_kernel + exact_scan_kernel (K1, experimental prefilter engine)"
         traffic, traffic_src = k1_traffic(split)
         out = dict(metric="propagated frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                    warmup=n_warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
@@ -339,6 +342,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--split", default=None, choices=["f16", "tf32"],
                     help="feature-bank split / tensor engine (default: f16 three-term; tf32 = 3xTF32)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "prefilter"],
+                    help="K1 engine: auto = exact tensor engine of the bank; prefilter = experimental fp16 prefilter + "
+                         "exact rescoring (profiles/r1_f_prefilter_engine.md)")
     ap.add_argument("--profile", action="store_true", help="kernels only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -114,9 +114,10 @@ extern "C" int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format,
   if (engine == FGVC_ENGINE_PREFILTER)
     FGVC_CHECK_ARG(can, "prefilter engine needs an F16 bank of unit rows, C %% 64 == 0, C <= 256, K <= 16, groups <= 8 "
                         "(format=%d unit_rows=%d C=%d K=%d groups=%d)", bank_format, unit_rows, C, K, groups);
-  const bool use = engine == FGVC_ENGINE_PREFILTER ||
-                   (engine == FGVC_ENGINE_AUTO && can && workspace != nullptr &&
-                    workspace_bytes >= tc16p_workspace_bytes(n_jobs, groups, H * W, K));
+  // AUTO stays on the exact engines: measured on B200 (profiles/r1_f_prefilter_engine.md) the prefilter's
+  // tensor work is 3x smaller but its epilogue (list insertions for 32 different queries per warp) is the
+  // bound, so it is not faster yet.  It is selected explicitly.
+  const bool use = engine == FGVC_ENGINE_PREFILTER;
   if (!use)
     return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
                               K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);

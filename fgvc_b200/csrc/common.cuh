@@ -160,6 +160,12 @@ int64_t tc16p_workspace_bytes(int n_jobs, int groups, int n_pix, int K);
 int launch_affinity_topk_tc16p(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                                const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv,
                                int32_t* ti, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int64_t chain_workspace_bytes(int n_jobs, int n_pix, int K);
+int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, const fgvc_job* jobs, int job_begin,
+                        int job_end, const int32_t* mem_label, int n_pix, float temperature, int flags, float* lab,
+                        int Lp, void* ws, int64_t ws_bytes, cudaStream_t st);
+int launch_labels_to_nchw_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int Lp, int L,
+                               int n_pix, float* maps_nchw, cudaStream_t st);
 int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
                        int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st);
 int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st);

@@ -100,9 +100,187 @@ static int launch_g(const float* tv, const int32_t* ti, int k_in, int groups, co
   return FGVC_OK;
 }
 
+
+// ------------------------------------------------------------------ the gather CHAIN
+// The recurrence of the reference loop (vanilla_tracker.py:345-394) lives only in the gather: frame t's
+// labels are a sparse combination of the labels of its memory frames.  One launch per frame costs ~20 us of
+// launch + drain latency for ~5 us of work, so a clip's chain is run by ONE persistent kernel:
+//   gather_weights_kernel : label-independent part for ALL jobs at once (merge groups, temperature, soft-max):
+//                           w[job][q][K], src_row[job][q][K] (label row = slot * n_pix + pixel);
+//   gather_chain_kernel   : cooperative launch, every CTA owns a fixed slice of the queries; per job it
+//                           gathers its slice, then all CTAs meet at a grid barrier (the next job reads rows
+//                           other CTAs wrote: label loads are ld.global.cg, stores are fenced before the barrier).
+template <int K>
+__global__ void __launch_bounds__(256)
+gather_weights_kernel(const float* __restrict__ tv, const int32_t* __restrict__ ti, int k_in, int groups,
+                      const fgvc_job* __restrict__ jobs, int job_begin, const int32_t* __restrict__ mem_label,
+                      int n_pix, float temperature, int flags, float* __restrict__ cw, int32_t* __restrict__ crow) {
+  const int jidx = job_begin + blockIdx.y;
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= n_pix) return;
+  const fgvc_job job = jobs[jidx];
+  TopK<K> top;
+  top.init();
+  for (int g = 0; g < groups; ++g) {
+    const int64_t o = (((int64_t)jidx * groups + g) * n_pix + q) * k_in;
+    for (int i = 0; i < k_in; ++i) {
+      const float v = __ldg(tv + o + i);
+      const int id = __ldg(ti + o + i);
+      if (id >= 0 && v > top.thr()) top.push(v, id);
+    }
+  }
+  float a[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+    a[i] = (flags & FGVC_SIM_L2) ? __fdiv_rn(2.f * top.v[i] - 1.f, temperature) : __fdiv_rn(top.v[i], temperature);
+  const float m = a[0];
+  float sum = 0.f;
+  if (flags & FGVC_WEIGHT_COSINE) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const float c = fmaxf(a[i], 0.f);
+      a[i] = (i < k_in && top.id[i] >= 0) ? c * c : 0.f;
+    }
+    sum = 1.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      a[i] = (i < k_in && top.id[i] >= 0) ? expf(a[i] - m) : 0.f;
+      sum += a[i];
+    }
+  }
+  const int64_t o = ((int64_t)blockIdx.y * n_pix + q) * K;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int id = top.id[i];
+    const bool ok = i < k_in && id >= 0;
+    int row = 0;
+    if (ok) {
+      const int pos = id / n_pix;
+      row = __ldg(mem_label + job.mem_begin + pos) * n_pix + (id - pos * n_pix);
+    }
+    cw[o + i] = ok ? ((flags & FGVC_WEIGHT_COSINE) ? a[i] : __fdiv_rn(a[i], sum)) : 0.f;
+    crow[o + i] = row;
+  }
+}
+
+constexpr int CH_Q = 32;      // queries staged per CTA pass
+
+template <int K>
+__global__ void __launch_bounds__(256)
+gather_chain_kernel(const float* __restrict__ cw, const int32_t* __restrict__ crow, const fgvc_job* __restrict__ jobs,
+                    int job_begin, int n_jobs, int n_pix, float* lab, int Lp, unsigned int* barrier) {
+  __shared__ float sw[CH_Q][K];
+  __shared__ int srow[CH_Q][K];
+  const int tid = threadIdx.x;
+  const int l4n = Lp / 4;
+  const float4* src = reinterpret_cast<const float4*>(lab);
+  // this CTA's queries: a contiguous slice (the same for every job)
+  const int per = (n_pix + gridDim.x - 1) / gridDim.x;
+  const int q_lo = blockIdx.x * per, q_hi = min(n_pix, q_lo + per);
+  for (int j = 0; j < n_jobs; ++j) {
+    const int out_slot = jobs[job_begin + j].out_slot;
+    float4* dst = reinterpret_cast<float4*>(lab) + (int64_t)out_slot * n_pix * l4n;
+    for (int q0 = q_lo; q0 < q_hi; q0 += CH_Q) {
+      const int nq = min(CH_Q, q_hi - q0);
+      __syncthreads();
+      for (int i = tid; i < nq * K; i += 256) {
+        const int64_t o = ((int64_t)j * n_pix + q0) * K + i;
+        (&sw[0][0])[i] = __ldg(cw + o);
+        (&srow[0][0])[i] = __ldg(crow + o);
+      }
+      __syncthreads();
+      for (int i = tid; i < nq * l4n; i += 256) {
+        const int q = i / l4n, c = i - q * l4n;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float w = sw[q][k];
+          if (w != 0.f) {
+            const float4 v = __ldcg(src + (int64_t)srow[q][k] * l4n + c);   // may have been written by another CTA
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+          }
+        }
+        dst[(int64_t)(q0 + q) * l4n + c] = acc;
+      }
+    }
+    // grid barrier: every CTA's stores of job j are visible before anyone starts job j + 1
+    if (j + 1 < n_jobs) {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(barrier, 1u);
+        const unsigned int want = (unsigned int)(j + 1) * gridDim.x;
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(barrier) : "memory");
+        } while (seen < want);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int64_t chain_workspace_bytes(int n_jobs, int n_pix, int K) {
+  const int Kt = K <= 4 ? 4 : (K <= 10 ? 10 : 16);
+  return (int64_t)n_jobs * n_pix * Kt * 8 + 256;
+}
+
+template <int K>
+static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int groups, const fgvc_job* jobs, int job_begin,
+                          int n, const int32_t* mem_label, int n_pix, float temperature, int flags, float* lab, int Lp,
+                          void* ws, cudaStream_t st) {
+  const int64_t cells = (int64_t)n * n_pix * K;
+  float* cw = reinterpret_cast<float*>(ws);
+  int32_t* crow = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ws) + cells * 4);
+  unsigned int* barrier = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + cells * 8);
+  FGVC_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+  dim3 gw(cdiv(n_pix, 256), n);
+  gather_weights_kernel<K><<<gw, 256, 0, st>>>(tv, ti, k_in, groups, jobs, job_begin, mem_label, n_pix, temperature,
+                                               flags, cw, crow);
+  FGVC_LAUNCH_CHECK();
+  // all CTAs must be co-resident (they spin on the grid barrier): cooperative launch, sized from the occupancy
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int dev = 0, sms = 0, occ = 0;
+    FGVC_CUDA(cudaGetDevice(&dev));
+    FGVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FGVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_chain_kernel<K>, 256, 0));
+    max_ctas = sms * (occ < 1 ? 1 : (occ > 2 ? 2 : occ));
+  }
+  const int l4n = Lp / 4;
+  // enough CTAs that one pass of CH_Q queries covers a slice when the rows are short; all of them for long rows
+  int ctas = (int)min((int64_t)max_ctas, max((int64_t)1, ((int64_t)n_pix * l4n + 255) / 256));
+  ctas = min(ctas, cdiv(n_pix, 1));
+  int n_jobs = n, jb = job_begin, npx = n_pix, lp = Lp;
+  void* args[] = {(void*)&cw, (void*)&crow, (void*)&jobs, (void*)&jb, (void*)&n_jobs, (void*)&npx, (void*)&lab,
+                  (void*)&lp, (void*)&barrier};
+  FGVC_CUDA(cudaLaunchCooperativeKernel((const void*)gather_chain_kernel<K>, dim3(ctas), dim3(256), args, 0, st));
+  fgvc::g_launches.fetch_add(1);
+  return FGVC_OK;
+}
+
+// K1b for the consecutive jobs [job_begin, job_end) as one persistent chain (see above)
+int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, const fgvc_job* jobs, int job_begin,
+                        int job_end, const int32_t* mem_label, int n_pix, float temperature, int flags, float* lab,
+                        int Lp, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int n = job_end - job_begin;
+  FGVC_CHECK_ARG(ws != nullptr && ws_bytes >= chain_workspace_bytes(n, n_pix, K),
+                 "gather chain: workspace of %lld bytes needed (fgvc_chain_workspace_bytes)",
+                 (long long)chain_workspace_bytes(n, n_pix, K));
+  if (K <= 4) return launch_chain_t<4>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
+  if (K <= 10) return launch_chain_t<10>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
+  return launch_chain_t<16>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
+}
+
 }  // namespace fgvc
 
 using namespace fgvc;
+
+extern "C" int64_t fgvc_chain_workspace_bytes(int32_t n_jobs, int32_t n_pix, int32_t K) {
+  return chain_workspace_bytes(n_jobs, n_pix, K);
+}
 
 extern "C" int fgvc_gather_labels(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                                   const fgvc_job* jobs, int32_t job_begin, int32_t job_end,

@@ -96,6 +96,27 @@ labels_to_nchw_kernel(const float* __restrict__ src, int Lp, int L, int n_pix, f
   }
 }
 
+// the same for the out_slots of jobs [job_begin, job_begin + gridDim.z): dst[slot][L][n_pix]
+__global__ void __launch_bounds__(256)
+labels_to_nchw_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int Lp, int L,
+                           int n_pix, float* __restrict__ maps) {
+  __shared__ float t[32][33];
+  const int slot = jobs[job_begin + blockIdx.z].out_slot;
+  const float* src = lab + (int64_t)slot * n_pix * Lp;
+  float* dst = maps + (int64_t)slot * L * n_pix;
+  const int p0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, l = l0 + tx;
+    t[j][tx] = (p < n_pix && l < Lp) ? __ldg(src + (int64_t)p * Lp + l) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int l = l0 + j, p = p0 + tx;
+    if (l < L && p < n_pix) dst[(int64_t)l * n_pix + p] = t[tx][j];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gaussian_labels_kernel(const float* __restrict__ pts, int P, int H, int W, int stride, float denom,
                        float* __restrict__ dst, int Lp) {
@@ -132,6 +153,18 @@ labels_harden_kernel(float* __restrict__ lab, int n_pix, int L, int Lp) {
 int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st) {
   labels_harden_kernel<<<cdiv(n_pix, 256), 256, 0, st>>>(lab_slot, n_pix, L, Lp);
   FGVC_LAUNCH_CHECK();
+  return FGVC_OK;
+}
+
+int launch_labels_to_nchw_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int Lp, int L,
+                               int n_pix, float* maps_nchw, cudaStream_t st) {
+  const int n = job_end - job_begin;
+  if (n <= 0) return FGVC_OK;
+  for (int z0 = 0; z0 < n; z0 += 65535) {
+    dim3 grid(cdiv(n_pix, 32), cdiv(L, 32), min(65535, n - z0));
+    labels_to_nchw_jobs_kernel<<<grid, 256, 0, st>>>(lab, jobs_dev, job_begin + z0, Lp, L, n_pix, maps_nchw);
+    FGVC_LAUNCH_CHECK();
+  }
   return FGVC_OK;
 }
 

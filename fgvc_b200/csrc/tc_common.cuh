@@ -30,23 +30,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The retry loop is
-// kept tiny (spinning warps share issue slots with the MMA / TMA warps of the same scheduler).
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded wait: a protocol bug traps (launch error) after 2 s of wall clock instead of hanging the GPU.  The retry
+// loop is kept tiny (spinning warps share issue slots with the MMA / TMA warps of the same scheduler).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 20)) __trap();
+    if ((++spins & 63u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
   }
 }
 // same for the epilogue warps, which wait about a box time (~1 us) per hand-off: sleep between
 // probes so that 16 waiting warps do not take issue slots from the warps that have work
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
   uint32_t spins = 0;
   do {
     __nanosleep(256);
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 63u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
   } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,

@@ -37,7 +37,11 @@ constexpr int TP_MAX_STAGES = 12;
 constexpr int TP_MAX_BH = 8;                   // N <= 128
 constexpr int TP_A_COL = 256;
 constexpr int TP_EPI_WG = 4;
-constexpr int TP_THREADS = 64 + 128 * TP_EPI_WG;
+constexpr int TP_THREADS = 128 + 128 * TP_EPI_WG;   // warpgroup 0 = {TMA producer, MMA issuer, 2 set-up warps}, then 4 epilogue warpgroups
+// Registers: the launch gives every thread 96 (640 x 96 <= 64 K); warpgroup 0 then hands most of its share
+// back (setmaxnreg.dec) and the epilogue warpgroups, which hold 32 accumulator values + the list, grow to 112:
+// 128 x 32 + 512 x 112 = 61440 = 640 x 96 (the pool setmaxnreg.inc draws from is what the launch allocated).
+constexpr int TP_REGS_CTRL = 32, TP_REGS_EPI = 112;
 constexpr int TP_MAX_BOXES = 3072;
 constexpr int TP_THR_BYTES = 2 * TP_EPI_WG * 128 * 4;   // seed / running threshold exchange: [2][4 warpgroups][128 queries]
 constexpr int TP_AUX_BYTES = 1024 + TP_THR_BYTES + 2 * TP_MAX_BOXES * 4;
@@ -87,42 +91,104 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// largest of the 16 accumulator values of a key row (masked-out keys included: a cheap screen)
-__device__ __forceinline__ float row_max16(const uint32_t* r) {
-  const float a = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-  const float b = fmax3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
-  const float c = fmax3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
-  const float d = fmax3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
-  const float e = fmax3(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]));
-  return fmax3(fmax3(a, b, c), fmax3(d, e, __uint_as_float(r[15])), -INFINITY);
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float max16(const float* v) {
+  const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
+  const float d = fmax3(v[9], v[10], v[11]), e = fmax3(v[12], v[13], v[14]);
+  return fmaxf(fmax3(a, b, c), fmax3(d, e, v[15]));
 }
 
-// Fold one key row (16 accumulator columns) into the thread's list.  `floor` = the query's prune level
-// (a lower bound of theta' minus the band): nothing at or below it can belong to the superset.
-// Returns true when this lane inserted something.
+// The epilogue's per-thread candidate list.  The epilogue is instruction-bound (every key row is "hot" for some of
+// the 32 queries of a warp), so the list is built for the cheapest possible insertion, not for order:
+//   * KP slots, UNSORTED; the low 4 mantissa bits of every stored value hold its slot number, so the minimum of the
+//     KP values (a 3-input min tree) is at once the K-th value and the slot the next insertion overwrites;
+//   * the 4 best values seen so far are kept on the side (a min/max cascade) for the bound shared between warpgroups;
+//   * one odd-even sort when the CTA is done.
+// Dropping 4 mantissa bits moves a' by <= 2^-19 relative, far inside the margin of FGVC_PREFILTER_EPS.
+constexpr uint32_t TP_NEG_BITS = 0xFF7FFFF0u;          // most negative finite float with the low 4 bits clear
+
 template <int KP>
-__device__ __forceinline__ bool scan_row(TopK<KP>& top, const uint32_t* r, uint32_t bits, int kbase, float floor,
-                                         int& n_rounds, int& n_ins) {
-  float v[16];
+struct MinList {
+  float v[KP];
+  int id[KP];
+  float thr;                 // min of v[]: the list's KP-th value (slot in the low 4 bits)
+  float t0, t1, t2, t3;      // best four values, descending
+  __device__ __forceinline__ void init() {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-  const float thr0 = fmaxf(top.thr(), floor);
-  uint32_t cand = 0;
+    for (int s = 0; s < KP; ++s) { v[s] = __uint_as_float(TP_NEG_BITS | (uint32_t)s); id[s] = -1; }
+    thr = v[0];
+    t0 = t1 = t2 = t3 = __uint_as_float(TP_NEG_BITS);
+  }
+  // caller guarantees x > thr
+  __device__ __forceinline__ void push(float x, int idx) {
+    const uint32_t slot = __float_as_uint(thr) & 15u;
+    const uint32_t xe = __float_as_uint(x) & ~15u;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
-  cand &= bits;
-  const bool any = cand != 0;
-  // warp-wide insertion rounds: every lane that still has a candidate takes its next one
-  while (__any_sync(0xffffffffu, cand != 0)) {
-    ++n_rounds;
-    if (cand) {
-      const int j = __ffs(cand) - 1;
-      cand &= cand - 1;
-      const float x = select16(v, j);
-      if (x > top.thr()) { top.push(x, kbase + j); ++n_ins; }
+    for (int s = 0; s < KP; ++s) {
+      const bool h = slot == (uint32_t)s;
+      v[s] = h ? __uint_as_float(xe | (uint32_t)s) : v[s];
+      id[s] = h ? idx : id[s];
+    }
+    float m = v[0];
+#pragma unroll
+    for (int s = 1; s + 1 < KP; s += 2) m = fmin3(m, v[s], v[s + 1]);
+    if ((KP & 1) == 0) m = fminf(m, v[KP - 1]);
+    thr = m;
+    float y, z = __uint_as_float(xe);
+    y = fminf(t0, z); t0 = fmaxf(t0, z); z = y;
+    y = fminf(t1, z); t1 = fmaxf(t1, z); z = y;
+    y = fminf(t2, z); t2 = fmaxf(t2, z); z = y;
+    t3 = fmaxf(t3, z);
+  }
+  __device__ __forceinline__ void sort_desc() {          // odd-even transposition, KP rounds
+#pragma unroll
+    for (int r = 0; r < KP; ++r) {
+#pragma unroll
+      for (int s = (r & 1); s + 1 < KP; s += 2) {
+        const bool sw = v[s] < v[s + 1];
+        const float a = v[s], b = v[s + 1];
+        const int ia = id[s], ib = id[s + 1];
+        v[s] = sw ? b : a; v[s + 1] = sw ? a : b;
+        id[s] = sw ? ib : ia; id[s + 1] = sw ? ia : ib;
+      }
     }
   }
-  return any;
+};
+
+// Fold one key row (16 accumulator columns) into the thread's list.  The column number goes into the low 4 bits of
+// every value, so a 3-input max tree yields the row's best value AND where it is; further candidates of the same
+// row are found by repeating the tree over the values strictly below the last one.  `floor` = the query's prune
+// level (a lower bound of theta' minus the band): nothing at or below it can belong to the superset.  `bits` = the
+// in-mask, in-image columns of this key row.  Returns true when this lane inserted something.
+template <int KP>
+__device__ __forceinline__ bool scan_row(MinList<KP>& top, const uint32_t* r, uint32_t bits, int kbase, float floor,
+                                         bool qvalid, int& n_rounds, int& n_ins) {
+  float enc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) enc[j] = __uint_as_float((r[j] & ~15u) | (uint32_t)j);
+  float mx = max16(enc);
+  bool changed = false;
+  float cur = INFINITY;
+#pragma unroll 1
+  for (int it = 0; it < 16; ++it) {                          // a row has 16 values: at most 16 extractions
+    const bool hot = qvalid && mx > fmaxf(top.thr, floor);
+    if (!__any_sync(0xffffffffu, hot)) break;
+    ++n_rounds;
+    if (hot) {
+      const int j = (int)(__float_as_uint(mx) & 15u);
+      if ((bits >> j) & 1u) { top.push(mx, kbase + j); changed = true; ++n_ins; }
+      cur = mx;
+    }
+    float e2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e2[j] = enc[j] < cur ? enc[j] : __uint_as_float(TP_NEG_BITS);
+    mx = max16(e2);
+  }
+  return changed;
 }
 
 // The order in which the three warp roles walk the (memory entry, key box) pairs of a CTA.
@@ -269,6 +335,8 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TP_REGS_CTRL));
   if (warp == 0) {
     // ================================ TMA producer ====================================
     if (elect_one()) {
@@ -339,9 +407,11 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
       }
     }
     __syncwarp();
+  }
   } else {
     // ================================== epilogue ======================================
-    const int wg = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TP_REGS_EPI));
+    const int wg = (warp - 4) >> 2;
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
     const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
@@ -362,7 +432,7 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
       __syncwarp();
       if (lane == 0) mbar_arrive(a_bar);
     }
-    TopK<KP> top;
+    MinList<KP> top;
     top.init();
     // ---- thresholds shared by the 4 threads of a query.  If warpgroup w publishes a value b_w such that
     // at least SH + 1 distinct candidates of ITS OWN share have a' >= b_w, then min_w b_w has
@@ -418,6 +488,7 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
     const float seed_floor = fminf(fminf(s_seed[m], s_seed[128 + m]), fminf(s_seed[256 + m], s_seed[384 + m])) - band;
     float floor_q = seed_floor;
     int st_rows = 0, st_hot = 0, st_rounds = 0, st_ins = 0;
+    uint32_t cached_bb = 0xffffffffu, mpk[4] = {0u, 0u, 0u, 0u};
     int buf = 0;
     uint32_t tph0 = 0, tph1 = 0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16);
@@ -461,35 +532,46 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
           const float run = fminf(fminf(s_run[m], s_run[128 + m]), fminf(s_run[256 + m], s_run[384 + m])) - band;
           floor_q = fmaxf(seed_floor, run);
         }
-        bool changed = false;
+        // in-mask, in-image columns of the thread's two key rows.  For masked entries the 8 row masks of a box
+        // depend on the box only, and in box-major order a box is visited once per entry: computed on box change.
+        uint32_t bits0, bits1;
+        if (masked) {
+          if (bb != cached_bb) {
+            cached_bb = bb;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const bool doit = rr ? do1 : do0;
-          if (!doit) continue;
-          const uint32_t* r = rr ? r1 : r0;
-          const int ky = rr ? ky1 : ky0;
-          // screen: nothing in the row (masked or not) beats the thread's current bar
-          const bool hot = qvalid && row_max16(r) > fmaxf(top.thr(), floor_q);
-          ++st_rows;
-          if (!__any_sync(0xffffffffu, hot)) continue;
-          ++st_hot;
-          // 16-bit interval mask of the in-mask, in-image keys of this key row
-          uint32_t bits = 0;
-          if (qvalid) {
-            int lo = 0, hi = p.W - 1;
-            if (masked) {
-              const int ady = abs(ky - qy);
-              const int hw = ady <= p.reach ? halfw[ady] : -1;
-              lo = hw < 0 ? 1 : max(qx - hw, 0);
-              hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
+            for (int i = 0; i < 4; ++i) {
+              uint32_t pk = 0;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int ky = by + 2 * i + h;
+                uint32_t bits = 0;
+                if (qvalid && 2 * i + h < p.BH && ky < p.H) {
+                  const int ady = abs(ky - qy);
+                  const int hw = ady <= p.reach ? halfw[ady] : -1;
+                  int lo = hw < 0 ? 1 : max(qx - hw, 0);
+                  int hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
+                  lo = max(lo - bx, 0);
+                  hi = min(hi - bx, 15);
+                  if (hi >= lo) bits = (2u << hi) - (1u << lo);
+                }
+                pk |= bits << (16 * h);
+              }
+              mpk[i] = pk;
             }
-            lo = max(lo - bx, 0);
-            hi = min(hi - bx, 15);
-            if (hi >= lo) bits = (2u << hi) - (1u << lo);
           }
-          changed |= scan_row<KP>(top, r, bits, pos_base + ky * p.W + bx, floor_q, st_rounds, st_ins);
+          const uint32_t lo_pair = (row0 & 2) ? mpk[1] : mpk[0], hi_pair = (row0 & 2) ? mpk[3] : mpk[2];
+          bits0 = (lo_pair >> (16 * (row0 & 1))) & 0xffffu;
+          bits1 = (hi_pair >> (16 * (row0 & 1))) & 0xffffu;
+        } else {
+          const int wcols = min(16, p.W - bx);
+          const uint32_t rowbits = qvalid ? ((1u << wcols) - 1u) : 0u;
+          bits0 = ky0 < p.H ? rowbits : 0u;
+          bits1 = ky1 < p.H ? rowbits : 0u;
         }
-        if (changed) s_run[wg * 128 + m] = top.v[SH];
+        bool changed = false;
+        if (do0) { ++st_rows; changed |= scan_row<KP>(top, r0, bits0, pos_base + ky0 * p.W + bx, floor_q, qvalid, st_rounds, st_ins); }
+        if (do1) { ++st_rows; changed |= scan_row<KP>(top, r1, bits1, pos_base + ky1 * p.W + bx, floor_q, qvalid, st_rounds, st_ins); }
+        if (changed) s_run[wg * 128 + m] = (SH == 0 ? top.t0 : (SH == 2 ? top.t2 : top.t3));
       }
     });
     if (p.exp_flags & 8) {
@@ -503,13 +585,14 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
     }
     // ---- the partial lists go out through the (now idle) ring so that the stores are coalesced:
     // workspace layout [job][group][query][warpgroup][KP]; a tile row of QW queries is contiguous
+    top.sort_desc();
     asm volatile("bar.sync 1, %0;" ::"n"(128 * TP_EPI_WG) : "memory");
     float* mv = reinterpret_cast<float*>(ring);
     int* mi = reinterpret_cast<int*>(ring + 128 * TP_EPI_WG * KP * 4);
 #pragma unroll
     for (int i = 0; i < KP; ++i) { mv[(m * TP_EPI_WG + wg) * KP + i] = top.v[i]; mi[(m * TP_EPI_WG + wg) * KP + i] = top.id[i]; }
     asm volatile("bar.sync 1, %0;" ::"n"(128 * TP_EPI_WG) : "memory");
-    const int et = threadIdx.x - 64;                       // 0 .. 511
+    const int et = threadIdx.x - 128;                       // 0 .. 511
     const int per_q = TP_EPI_WG * KP;
     const int qw_valid = min(p.QW, p.W - qx0);
     const int row_elems = qw_valid * per_q;
@@ -677,20 +760,23 @@ rescore_kernel(const __half* __restrict__ bank, const RescoreParams p) {
     if ((i0 & 31) == lane) { if (i0 < 32) { ev0 = va; ei0 = ia; } else { ev1 = va; ei1 = ia; } }
     if (i0 + 1 < n_c && ((i0 + 1) & 31) == lane) { if (i0 + 1 < 32) { ev0 = vb; ei0 = ib; } else { ev1 = vb; ei1 = ib; } }
   }
-  // exact top-k of the candidates: k rounds of warp arg-max (ties: the earlier candidate)
+  // exact top-k of the candidates: k rounds of warp arg-max.  Exact ties (the same frame twice in the memory
+  // list) go to the smaller candidate index, so the result does not depend on the order of the lists.
   float out_v = -INFINITY;
   int out_i = -1;
   for (int r = 0; r < p.k_out; ++r) {
-    const bool first = ev0 >= ev1;                           // a lane's better entry (slot 0 on ties)
+    const bool first = ev0 > ev1 || (ev0 == ev1 && (uint32_t)ei0 <= (uint32_t)ei1);   // id -1 sorts last
     const float x = first ? ev0 : ev1;
-    const bool have = (first ? ei0 : ei1) >= 0;
+    const int xi = first ? ei0 : ei1;
+    const bool have = xi >= 0;
     const float mx = warp_max(have ? x : -INFINITY);
-    const uint32_t who = __ballot_sync(0xffffffffu, have && x == mx);
-    if (who == 0) break;
-    const int src = __ffs(who) - 1;
-    const int id = __shfl_sync(0xffffffffu, first ? ei0 : ei1, src);
-    if (lane == r) { out_v = mx; out_i = id; }
-    if (lane == src) { if (first) { ev0 = -INFINITY; ei0 = -1; } else { ev1 = -INFINITY; ei1 = -1; } }
+    const bool tied = have && x == mx;
+    if (!__any_sync(0xffffffffu, tied)) break;
+    uint32_t best = tied ? (uint32_t)xi : 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == r) { out_v = mx; out_i = (int)best; }
+    if (tied && (uint32_t)xi == best) { if (first) { ev0 = -INFINITY; ei0 = -1; } else { ev1 = -INFINITY; ei1 = -1; } }
   }
   const int64_t o0 = ((int64_t)jidx * p.groups * p.n_pix + q) * p.k_out;
   if (lane < p.k_out) { p.tv[o0 + lane] = out_v; p.ti[o0 + lane] = out_i; }

@@ -227,8 +227,8 @@ def _workspace(dev, nbytes):
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
                   job_range=None):
     """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch.  ``AUTO``
-    = the prefilter engine (one fp16 tensor MAC per pair + exact rescoring) for F16 banks of unit rows, else
-    the exact tensor engine of the bank format, else the CUDA-core engine."""
+    = the exact tensor engine of the bank format, else the CUDA-core engine; ``ENGINE_PREFILTER`` (one fp16
+    tensor MAC per pair + exact rescoring; F16 banks of unit rows) is explicit."""
     dev = bank.buf.device
     jobs, mem_feat, _ = table.device(dev)
     if groups is None:
@@ -240,7 +240,7 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
     ws, ws_bytes = None, 0
-    if engine in (_lib.ENGINE_AUTO, _lib.ENGINE_PREFILTER) and bank.unit_rows and \
+    if engine == _lib.ENGINE_PREFILTER and bank.unit_rows and \
             _lib.load().fgvc_prefilter_supported(bank.fmt, bank.H, bank.W, bank.C, int(K), int(groups)):
         ws_bytes = int(_lib.load().fgvc_affinity_topk_workspace_bytes(j1 - j0, int(groups), lists.n_query, int(K)))
         ws = _workspace(dev, ws_bytes)

@@ -75,8 +75,8 @@ typedef enum fgvc_engine {
   /* F16 bank with UNIT rows (K0 with normalize = 1) only: one fp16 tensor MAC per (query, key) pair finds a
    * rigorous superset of the top-K (|error| <= 1.25e-3 => band of 2.5e-3 below the K-th value), the superset is
    * re-scored exactly in fp32 and the exact top-K is taken from it; queries whose superset may be
-   * incomplete are re-done by an exact scan.  Same results as TCGEN05 at a third of the tensor work.
-   * Needs the workspace of fgvc_affinity_topk_ws. */
+   * incomplete are re-done by an exact scan.  Same results as TCGEN05 at a third of the tensor work
+   * (experimental: explicit only, AUTO never picks it).  Needs the workspace of fgvc_affinity_topk_ws. */
   FGVC_ENGINE_PREFILTER = 3
 } fgvc_engine;
 
@@ -142,10 +142,11 @@ FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int3
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
 
-/* Same with a caller-owned workspace: needed by FGVC_ENGINE_PREFILTER (candidate lists + the queue of
- * queries for the exact scan); with a workspace AUTO prefers the prefilter engine when
- * `unit_rows` != 0 (every bank slot used was written by K0 with normalize = 1), the bank is F16 and
- * the shape allows (C % 64 == 0, C <= 256, groups <= 8).  fgvc_affinity_topk_workspace_bytes gives the size. */
+/* Same with a caller-owned workspace, which FGVC_ENGINE_PREFILTER needs (candidate lists + the queue of
+ * queries for the exact scan).  `unit_rows` != 0 asserts that every bank slot used was written by K0 with
+ * normalize = 1 (the prefilter's error bound needs unit vectors; it refuses otherwise).  Every other engine
+ * value behaves exactly like fgvc_affinity_topk and ignores the workspace.
+ * fgvc_affinity_topk_workspace_bytes gives the size. */
 FGVC_API int64_t fgvc_affinity_topk_workspace_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K);
 FGVC_API int fgvc_prefilter_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K, int32_t groups);
 FGVC_API int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,

@@ -9,7 +9,8 @@ from fgvc_b200 import engine
 dev = torch.device("cuda", 0)
 feats, onehot = bench.build_inputs(dev, 1000)
 W = bench.WORK
-clip = engine.MaskClipPropagator(W["clip_frames"], W["channels"], *W["feat_hw"], W["objects"], W["image_hw"], bench.CFG, dev)
+clip = engine.MaskClipPropagator(W["clip_frames"], W["channels"], *W["feat_hw"], W["objects"], W["image_hw"], bench.CFG, dev,
+                                 engine_id=engine._lib.ENGINE_PREFILTER)
 clip.run(feats, onehot, want_maps=False)
 torch.cuda.synchronize()
 ws = engine._WORKSPACES[(0, torch.cuda.current_stream().cuda_stream)]

@@ -12,7 +12,8 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
                                    int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                                    float temperature, int32_t flags,
                                    float* lab_bank, int32_t Lp, int32_t L, int32_t out_h, int32_t out_w,
-                                   float* scratch_minmax, uint8_t* masks, float* maps_nchw, void* stream) {
+                                   float* scratch_minmax, uint8_t* masks, float* maps_nchw, void* chain_ws,
+                                   int64_t chain_ws_bytes, void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && masks && scratch_minmax && lab_bank, "fgvc_mask_clip_tail: null pointer");
   FGVC_CHECK_ARG(L > 0 && L <= 255 && Lp >= L && Lp % 4 == 0, "fgvc_mask_clip_tail: bad label sizes");
   const int n_pix = H * W;
@@ -40,14 +41,25 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
     return FGVC_OK;
   }
   // the recurrence lives only in the gather: run the chain first ...
-  for (int j = job_begin; j < job_end; ++j) {
-    int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
-                                temperature, flags, lab_bank, Lp, stream);
+  if (chain_ws != nullptr && job_end - job_begin > 1) {
+    // ... as ONE persistent kernel with a grid barrier per frame (gather.cu)
+    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, n_pix,
+                                 temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
     if (rc) return rc;
     if (maps_nchw) {
-      const int slot = jobs_host[j].out_slot;
-      rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
+      rc = launch_labels_to_nchw_jobs(lab_bank, jobs_dev, job_begin, job_end, Lp, L, n_pix, maps_nchw, st);
       if (rc) return rc;
+    }
+  } else {
+    for (int j = job_begin; j < job_end; ++j) {
+      int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
+                                  temperature, flags, lab_bank, Lp, stream);
+      if (rc) return rc;
+      if (maps_nchw) {
+        const int slot = jobs_host[j].out_slot;
+        rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
+        if (rc) return rc;
+      }
     }
   }
   // ... then decode every frame of the range in two batched launches (scratch: [n_jobs][2L] words)
@@ -64,19 +76,29 @@ extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_i
                                     int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                                     float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
                                     int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
-                                    void* stream) {
+                                    void* chain_ws, int64_t chain_ws_bytes, void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && maps_nchw && coords && lab_bank, "fgvc_point_clip_tail: null pointer");
   FGVC_CHECK_ARG(job_end > job_begin, "fgvc_point_clip_tail: empty job range");
   const int n_pix = H * W;
   const int slot0 = jobs_host[job_begin].out_slot;
-  for (int j = job_begin; j < job_end; ++j) {
-    const int slot = jobs_host[j].out_slot;
-    FGVC_CHECK_ARG(slot == slot0 + (j - job_begin), "fgvc_point_clip_tail: out_slots must be consecutive");
-    int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
-                                temperature, flags, lab_bank, Lp, stream);
+  for (int j = job_begin; j < job_end; ++j)
+    FGVC_CHECK_ARG(jobs_host[j].out_slot == slot0 + (j - job_begin), "fgvc_point_clip_tail: out_slots must be consecutive");
+  if (chain_ws != nullptr && job_end - job_begin > 1) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, n_pix,
+                                 temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
     if (rc) return rc;
-    rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
+    rc = launch_labels_to_nchw_jobs(lab_bank, jobs_dev, job_begin, job_end, Lp, L, n_pix, maps_nchw, st);
     if (rc) return rc;
+  } else {
+    for (int j = job_begin; j < job_end; ++j) {
+      const int slot = jobs_host[j].out_slot;
+      int rc = fgvc_gather_labels(topk_val, topk_idx, K, groups, jobs_dev, j, j + 1, mem_label_slot, n_pix,
+                                  temperature, flags, lab_bank, Lp, stream);
+      if (rc) return rc;
+      rc = fgvc_labels_to_nchw(lab_bank, slot, Lp, L, n_pix, maps_nchw + (int64_t)slot * L * n_pix, stream);
+      if (rc) return rc;
+    }
   }
   return fgvc_heatmap_coords(maps_nchw + (int64_t)slot0 * L * n_pix, (job_end - job_begin) * L, H, W, out_h, out_w,
                              coord_topk, coords + (int64_t)slot0 * L * 2, stream);

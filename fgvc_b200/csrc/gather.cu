@@ -247,12 +247,13 @@ static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int grou
     FGVC_CUDA(cudaGetDevice(&dev));
     FGVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FGVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_chain_kernel<K>, 256, 0));
-    max_ctas = sms * (occ < 1 ? 1 : (occ > 2 ? 2 : occ));
+    max_ctas = sms * (occ < 1 ? 1 : occ);
   }
   const int l4n = Lp / 4;
-  // enough CTAs that one pass of CH_Q queries covers a slice when the rows are short; all of them for long rows
-  int ctas = (int)min((int64_t)max_ctas, max((int64_t)1, ((int64_t)n_pix * l4n + 255) / 256));
-  ctas = min(ctas, cdiv(n_pix, 1));
+  // latency-bound (a few microseconds per frame): as many CTAs as can be co-resident, so that a CTA's slice is
+  // one pass of <= CH_Q queries whenever possible
+  // (short label rows: ~2 CTAs per SM; long rows want every resident thread for memory-level parallelism)
+  const int ctas = (int)min((int64_t)max_ctas, max((int64_t)1, ((int64_t)n_pix * l4n + 63) / 64));
   int n_jobs = n, jb = job_begin, npx = n_pix, lp = Lp;
   void* args[] = {(void*)&cw, (void*)&crow, (void*)&jobs, (void*)&jb, (void*)&n_jobs, (void*)&npx, (void*)&lab,
                   (void*)&lp, (void*)&barrier};

@@ -5,6 +5,7 @@ Vocabulary follows the reference (``feat_bank`` / ``seg_bank`` of
 mmpt/models/trackers/vanilla_tracker.py:318-394): a *slot* holds one frame.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -211,17 +212,37 @@ class TopKLists:
 
 
 _WORKSPACES = {}
+_CHAIN_WS = {}
+
+
+def _ws_key(dev):
+    dev = torch.device(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return (idx, torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _workspace(dev, nbytes):
     """Caller-owned scratch of the prefilter engine, one per (device, stream), grown on demand.  Work on
     one stream is ordered, so consecutive K1 launches can share it."""
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    key = _ws_key(dev)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         _WORKSPACES[key] = ws
     return ws
+
+
+def chain_workspace(dev, n_jobs, n_pix, K, flags=0):
+    """(pointer, bytes) of the scratch that lets a clip tail run its gather chain as one persistent kernel;
+    (None, 0) = per-frame launches (hard propagation decodes between frames, single-frame ranges gain nothing)."""
+    if n_jobs <= 1 or (flags & _lib.HARD_PROP) or os.environ.get("FGVC_NO_CHAIN") == "1":
+        return None, 0
+    nbytes = int(_lib.load().fgvc_chain_workspace_bytes(int(n_jobs), int(n_pix), int(K)))
+    ws = _CHAIN_WS.get(_ws_key(dev))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _CHAIN_WS[_ws_key(dev)] = ws
+    return ptr(ws), nbytes
 
 
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
@@ -381,7 +402,8 @@ class MaskClipPropagator:
         call("fgvc_mask_clip_tail", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups,
              ptr(jobs), ptr(self.jobs_host), j0, j1, ptr(mem_label), self.H, self.W,
              self.temperature, self.flags, ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
-             self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None, stream_ptr())
+             self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None,
+             *chain_workspace(self.device, j1 - j0, self.H * self.W, lists.K, self.flags), stream_ptr())
 
     def _k1(self, j0, j1, lists=None):
         cfg = self.cfg

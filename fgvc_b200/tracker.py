@@ -126,7 +126,8 @@ class VanillaTracker(nn.Module):
                 _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
                           _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
                           temperature, flags, _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
-                          _lib.ptr(coords), _lib.stream_ptr())
+                          _lib.ptr(coords), *engine.chain_workspace(dev, T - t0 - 1, Hf * Wf, lists.K, flags),
+                          _lib.stream_ptr())
             outs.append(coords.double())
         return outs
 

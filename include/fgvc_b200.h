@@ -201,18 +201,22 @@ FGVC_API int fgvc_decode_masks_pixmajor(const float* lab_bank, int32_t slot, int
  *  point tail: the K1b gather chain over jobs [job_begin, job_end) with an NCHW copy of every frame
  *              into maps_nchw[slot][L][H*W], then ONE K3 launch over all their (frame, point) maps
  *              into coords[slot][L][2]; the out_slots of the range must be consecutive. */
+/* chain_ws (optional, fgvc_chain_workspace_bytes(job_end - job_begin, H*W, K) bytes): with it the gather chain of a
+ * range runs as ONE persistent cooperative kernel (label-independent weights for all frames first, then one grid
+ * barrier per frame) instead of one launch per frame; NULL keeps the per-frame launches.  Same results. */
+FGVC_API int64_t fgvc_chain_workspace_bytes(int32_t n_jobs, int32_t n_pix, int32_t K);
 FGVC_API int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                         const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                         int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                         float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L,
                         int32_t out_h, int32_t out_w, float* scratch_minmax, uint8_t* masks,
-                        float* maps_nchw, void* stream);
+                        float* maps_nchw, void* chain_ws, int64_t chain_ws_bytes, void* stream);
 FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                          const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                          int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                          float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L,
                          int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
-                         float* coords, void* stream);
+                         float* coords, void* chain_ws, int64_t chain_ws_bytes, void* stream);
 
 /* K2 -- coarse-to-fine propagation (local_attention.py:721-880), single query frame.
  * Coarse stage = per-memory-frame masked argmax on the coarse bank (K1 with K=1 per

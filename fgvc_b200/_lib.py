@@ -48,6 +48,7 @@ SIGNATURES = {
     "fgvc_affinity_topk_ws": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, I, P, L64, P]),
     "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
     "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, I, P, I, P]),
+    "fgvc_dense_propagate": (I, [P, I, I, I, I, P, I, P, P, I, I, F, I, P, I, P]),
     "fgvc_heatmap_coords": (I, [P, I, I, I, I, I, I, P, P]),
     "fgvc_gaussian_coords": (I, [P, I, I, I, F, I, P, P]),
     "fgvc_decode_masks": (I, [P, I, I, I, I, I, P, P, P]),

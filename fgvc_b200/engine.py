@@ -300,6 +300,17 @@ def gather_labels(lists, table, job_begin, job_end, labels, temperature, flags=0
          labels.Lp, stream_ptr())
 
 
+def dense_propagate(bank, table, job_begin, job_end, labels, radius, temperature, flags=0, mask_mode="circle"):
+    """topk=None (local_attention.py:376-383): soft-max / clamp^2 over ALL allowed candidates, written straight
+    into each job's out_slot of ``labels``."""
+    dev = labels.buf.device
+    jobs, mem_feat, mem_label = table.device(dev)
+    mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
+    call("fgvc_dense_propagate", ptr(bank.buf), bank.fmt, bank.H, bank.W, bank.C,
+         ctypes.c_void_p(jobs.data_ptr() + 16 * int(job_begin)), int(job_end - job_begin), ptr(mem_feat), ptr(mem_label),
+         int(radius), mode, float(temperature), int(flags), ptr(labels.buf), labels.Lp, stream_ptr())
+
+
 def heatmap_coords(maps, out_hw, topk=5):
     """K3: maps [n,H,W] fp32 CUDA -> [n,2] (x,y) after bilinear up-sampling to out_hw."""
     maps = maps.contiguous()

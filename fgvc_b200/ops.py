@@ -8,8 +8,8 @@ Reference interfaces (paths relative to the FGVC repository):
   spatial_neighbor                mmpt/models/common/affinity_utils.py:75-112
 
 Differences, all loud: N must be 1 (the reference driver asserts it and its gather
-indexes batch 0 only, local_attention.py:360-362); ``topk=None`` (dense soft-max), ``topk > 16`` and
-``sim_mode='l2-distance'`` without normalisation raise NotImplementedError; ``step`` is accepted and
+indexes batch 0 only, local_attention.py:360-362); ``topk > 16`` and ``sim_mode='l2-distance'``
+without normalisation raise NotImplementedError (``topk=None``, the dense soft-max, runs as a flash-style kernel); ``step`` is accepted and
 ignored (nothing is chunked: the affinity never exists in HBM); a ``mask`` tensor must be
 one that ``spatial_neighbor`` produces (its radius is recovered and verified), because the
 kernels evaluate the mask analytically.  There is no CPU fallback.
@@ -98,9 +98,7 @@ def _check_common(query, key, value, mode, sim_mode, topk):
     if query.size(0) != 1:
         raise NotImplementedError("batch size must be 1 (as in the reference driver, vanilla_tracker.py:134)")
     assert sim_mode in ["dot_product", "l2-distance"]
-    if topk is None:
-        raise NotImplementedError("topk=None (dense soft-max) is not built")
-    if not (1 <= topk <= 16):
+    if topk is not None and not (1 <= topk <= 16):
         raise NotImplementedError("topk must be in [1, 16]")
     _lib.require_cuda()
     for t in (query, key, value):
@@ -131,8 +129,11 @@ def _propagate(query, key, value, radius, mask_mode, temperature, topk, normaliz
     table = JobTable()
     table.add(T, list(range(T)), list(range(T)), T, unmasked=non_mask_len if radius is not None else T)
     r = radius if radius is not None else 1
-    lists = engine.affinity_topk(feats, table, r, topk, mask_mode, groups=groups, engine=engine_id)
-    engine.gather_labels(lists, table, 0, 1, labels, temperature, flags)
+    if topk is None:      # dense soft-max over every allowed candidate (local_attention.py:376-383)
+        engine.dense_propagate(feats, table, 0, 1, labels, r, temperature, flags, mask_mode)
+    else:
+        lists = engine.affinity_topk(feats, table, r, topk, mask_mode, groups=groups, engine=engine_id)
+        engine.gather_labels(lists, table, 0, 1, labels, temperature, flags)
     return labels.get_nchw(T).view(1, L, Hq, Wq)
 
 
@@ -178,6 +179,8 @@ def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask
                                    sim_mode="dot_product", radius_fine=12, engine_id=_lib.ENGINE_AUTO, split=None):
     """Coarse-to-fine propagation (local_attention.py:721-880).  ``value`` lives on the FINE
     grid [1,L,T,s*Hk,s*Wk]; the output on the COARSE query grid [1,L,Hq,Wq]."""
+    if topk is None:
+        raise NotImplementedError("masked_attention_efficient_c2f: topk=None is not built (the fine stage selects)")
     _check_common(query, key, value, mode, sim_mode, topk)
     if mode != "softmax" or sim_mode != "dot_product":
         raise NotImplementedError("c2f is built for mode='softmax', sim_mode='dot_product'")

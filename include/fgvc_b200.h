@@ -172,6 +172,14 @@ FGVC_API int fgvc_gather_labels(const float* topk_val, const int32_t* topk_idx, 
                        const int32_t* mem_label_slot, int32_t n_pix, float temperature, int32_t flags,
                        float* lab_bank, int32_t Lp, void* stream);
 
+/* Dense propagation -- topk = None (local_attention.py:376-383): weights = soft-max (or clamp(a,0)^2 with
+ * FGVC_WEIGHT_COSINE) over ALL allowed candidates; flash-style, fp32 on the CUDA cores, writes each job's
+ * out_slot of the label bank directly.  jobs[0..n_jobs) must not read each other's out_slot. */
+FGVC_API int fgvc_dense_propagate(const void* feat_bank, int32_t bank_format, int32_t H, int32_t W, int32_t C,
+                         const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                         const int32_t* mem_label_slot, int32_t radius, int32_t mask_mode, float temperature,
+                         int32_t flags, float* lab_bank, int32_t Lp, void* stream);
+
 /* K3 -- F.interpolate(bilinear, align_corners=False) to (out_h,out_w) fused with img2coord
  * (vanilla_tracker.py:396-400, :172-191): top-5 soft-argmax, all-zero map -> -1.
  * maps: n_maps channel-major maps [H*W]; out_xy: [n_maps][2]. */

@@ -62,6 +62,26 @@ def gen_propagate(ref):
     return cases
 
 
+def gen_dense(ref):
+    """topk=None (dense soft-max / clamp^2 over all allowed candidates, local_attention.py:376-383)."""
+    g = torch.Generator().manual_seed(311)
+    H, W, C, T, L, nr = 11, 13, 32, 3, 5, 8
+    f = _coherent_feats(g, T + 1, C, H, W)
+    q, kf = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+    v = torch.rand(1, L, T, H, W, generator=g)
+    mask = ref.spatial_neighbor(1, H, W, neighbor_range=nr, device="cpu", dtype=torch.float32)
+    d = dict(q=q.numpy(), k=kf.numpy(), v=v.numpy(), neighbor_range=nr, temperature=0.07)
+    d["softmax"] = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=None, step=64).numpy()
+    d["softmax_nonmask1"] = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=None, step=64,
+                                                           non_mask_len=1).numpy()
+    d["cosine"] = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=None, step=64,
+                                                 mode="cosine").numpy()
+    d["l2"] = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=None, step=64,
+                                             sim_mode="l2-distance").numpy()
+    d["nomask"] = ref.masked_attention_efficient(q, kf, v, None, temperature=0.07, topk=None, step=64).numpy()
+    np.savez_compressed(os.path.join(OUT, "prop_dense.npz"), **d)
+
+
 def gen_masks(ref):
     d = {}
     for (H, W, nr) in [(6, 7, 4), (9, 5, 7), (12, 14, 8)]:
@@ -164,6 +184,7 @@ def main():
     torch.set_num_threads(8)
     ref = ref_loader.load_functions()
     print("propagate:", gen_propagate(ref))
+    gen_dense(ref)
     gen_masks(ref)
     gen_c2f(ref)
     gen_legacy(ref)

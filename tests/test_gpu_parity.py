@@ -119,6 +119,40 @@ def test_plain_mask_tensor_and_none_mask(golden_dir):
     assert (got.cpu() - want).abs().max() < TIGHT
 
 
+# ------------------------------------------------------------------ dense mode (topk=None)
+@pytest.mark.parametrize("split", ["tf32", "f16"])
+def test_dense_mode_matches_reference_golden(golden_dir, split):
+    """topk=None: soft-max / clamp^2 over ALL allowed candidates (local_attention.py:376-383), flash-style kernel."""
+    import fgvc_b200
+    d = np.load(os.path.join(golden_dir, "prop_dense.npz"))
+    q, k, v = (torch.from_numpy(d[x]).cuda() for x in "qkv")
+    H, W = q.shape[2:]
+    mask = fgvc_b200.spatial_neighbor(1, H, W, int(d["neighbor_range"]), q.device, torch.float32)
+    for name, kw in (("softmax", {}), ("softmax_nonmask1", dict(non_mask_len=1)), ("cosine", dict(mode="cosine")),
+                     ("l2", dict(sim_mode="l2-distance"))):
+        got = fgvc_b200.masked_attention_efficient(q, k, v, mask, temperature=0.07, topk=None, split=split, **kw)
+        want = torch.from_numpy(d[name])
+        assert torch.allclose(got.cpu(), want, atol=2e-5, rtol=2e-5), name
+    got = fgvc_b200.masked_attention_efficient(q, k, v, None, temperature=0.07, topk=None, split=split)
+    assert torch.allclose(got.cpu(), torch.from_numpy(d["nomask"]), atol=2e-5, rtol=2e-5)
+
+
+def test_dense_mode_ragged_many_channels():
+    """L > 64 (two label chunks), map not a multiple of the tile, radius v2 form, C = 96."""
+    import fgvc_b200
+    g = torch.Generator().manual_seed(91)
+    H, W, C, T, L = 19, 27, 96, 2, 70
+    f = _coherent(g, T + 1, C, H, W)
+    q, k = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+    v = torch.rand(1, L, T, H, W, generator=g)
+    got = fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 5, temperature=0.07, topk=None)
+    want = O.propagate_port(q, k, v, radius=5, temperature=0.07, topk=None)
+    assert torch.allclose(got.cpu(), want, atol=2e-5, rtol=2e-5)
+    ones = torch.ones(1, 3, T, H, W)
+    got = fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), ones.cuda(), 5, temperature=0.07, topk=None)
+    assert (got - 1).abs().max() < 1e-5                       # soft-max weights sum to one
+
+
 # ------------------------------------------------------------- oracle, seeded inputs
 CASES = [
     # H, W, C, T, L, radius, topk, non_mask_len, mask_mode

@@ -5,6 +5,8 @@ import sys
 
 import numpy as np
 import pytest
+
+import fgvc_b200
 import torch
 import torch.multiprocessing as mp
 
@@ -74,10 +76,12 @@ def test_mask_radius_recovered_from_plain_tensor():
 
 def test_unsupported_modes_raise_loudly():
     q, k, v = torch.randn(1, 32, 4, 4), torch.randn(1, 32, 1, 4, 4), torch.rand(1, 2, 1, 4, 4)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(fgvc_b200.FgvcError):                 # topk=None is built (dense kernel) but there is no CPU path
         ops.masked_attention_efficient(q, k, v, None, topk=None)
     with pytest.raises(NotImplementedError):
         ops.masked_attention_efficient(q, k, v, None, topk=17)
+    with pytest.raises(NotImplementedError):
+        ops.masked_attention_efficient_c2f(q, k, q, k, v, None, topk=None)
     with pytest.raises(NotImplementedError):
         engine.sim_params(None, 32, 0.07, sim_mode="l2-distance", normalize=False)
     assert engine.sim_params(None, 64, 0.07, mode="cosine", sim_mode="l2-distance") == (8.0, 3)

@@ -30,6 +30,25 @@ def test_propagate_port_matches_reference(golden_dir, name):
     assert torch.allclose(out2, torch.from_numpy(d["out_v2"]), atol=2e-6, rtol=0)
 
 
+DENSE = [("softmax", {}), ("softmax_nonmask1", dict(non_mask_len=1)), ("cosine", dict(mode="cosine")),
+         ("l2", dict(sim_mode="l2-distance")), ("nomask", None)]
+
+
+@pytest.mark.parametrize("name,kw", DENSE)
+def test_dense_port_matches_reference(golden_dir, name, kw):
+    """topk=None: weights over ALL allowed candidates (local_attention.py:376-383)."""
+    d = _load(golden_dir, "prop_dense.npz")
+    q, k, v = (torch.from_numpy(d[x]) for x in "qkv")
+    H, W = q.shape[2:]
+    if kw is None:
+        out = O.propagate_port(q, k, v, mask=None, temperature=0.07, topk=None)
+    else:
+        out = O.propagate_port(q, k, v, mask=O.neighbor_mask(H, W, int(d["neighbor_range"])), temperature=0.07,
+                               topk=None, **kw)
+    want = torch.from_numpy(d[name])
+    assert torch.allclose(out, want, atol=2e-6, rtol=1e-6)
+
+
 @pytest.mark.parametrize("name", PROP)
 def test_propagate_exact_matches_reference(golden_dir, name):
     d = _load(golden_dir, f"prop_{name}.npz")

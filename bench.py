@@ -61,6 +61,45 @@ def algorithmic_work():
     return dict(flops_per_step=flops, in_mask_pairs=pairs, mem_entries=entries)
 
 
+def dense_pairs(H, W, r, split="f16"):
+    """(query, key) pairs the tensor engine actually multiplies: 128-query tiles x the key boxes (16 x BH pixels)
+    of their radius halo that some query of the tile can see.  Same geometry choices as the launcher
+    (csrc/topk_tc16.cu: tile orientation and BH by halo cost; corner boxes skipped)."""
+    reach = r - 1
+    max_bh = 4 if split == "f16" else 8
+
+    def box_cost(rows, bh):
+        return -(-rows // bh) * (16 * bh + 24)
+
+    def pick_bh(rows):
+        best = max_bh
+        for bh in range(max_bh - 1, 0, -1):
+            if box_cost(rows, bh) < box_cost(rows, best):
+                best = bh
+        return best
+
+    def halo_cost(qh, qw):
+        rows, cols = min(H, qh + 2 * reach), min(W, qw + 2 * reach)
+        return (-(-H // qh)) * (-(-W // qw)) * box_cost(rows, pick_bh(rows)) * (-(-cols // 16))
+
+    QH, QW = (16, 8) if halo_cost(16, 8) < halo_cost(8, 16) else (8, 16)
+    bh = pick_bh(min(H, QH + 2 * reach))
+    total = 0
+    for qy0 in range(0, H, QH):
+        for qx0 in range(0, W, QW):
+            y_lo, y_hi = max(0, qy0 - reach), min(H - 1, qy0 + QH - 1 + reach)
+            x_lo, x_hi = max(0, qx0 - reach), min(W - 1, qx0 + QW - 1 + reach)
+            qy1, qx1 = min(H - 1, qy0 + QH - 1), min(W - 1, qx0 + QW - 1)
+            for by in range(y_lo, y_hi + 1, bh):
+                for bx in range(x_lo, x_hi + 1, 16):
+                    by1, bx1 = min(H - 1, by + bh - 1), min(W - 1, bx + 15)
+                    dy = max(0, by - qy1, qy0 - by1)
+                    dx = max(0, bx - qx1, qx0 - bx1)
+                    if dy * dy + dx * dx < r * r:
+                        total += 128 * 16 * bh
+    return total
+
+
 def k1_traffic(split):
     """DRAM bytes of one K1 launch of this workload from the committed ncu capture (or None)."""
     try:
@@ -256,7 +295,14 @@ def run_ours(args):
                                  k1_share_of_step=k1 / (ms / args.steps),
                                  peak_source=f"{pk['src']} bf16 sustained {pk['bf16']} TF/s" + (" / 3 (three fp16 MMAs per MAC)" if split == "f16"
                                              else " / 2 (tf32) / 3 (3xTF32)"),
-                                 flops_per_launch=work["flops_per_step"]),
+                                 flops_per_launch=work["flops_per_step"],
+                                 # geometry: a 128-query tile multiplies the union of its queries' circles, in whole
+                                 # key boxes.  frac_dense = what the tensor pipe itself sustains (dense MACs / peak)
+                                 tile_overhead=dense_pairs(H, W, WORK["neighbor_range"] // 2, split) / work["in_mask_pairs"],
+                                 frac_dense=achieved / peak * dense_pairs(H, W, WORK["neighbor_range"] // 2, split)
+                                 / work["in_mask_pairs"],
+                                 # SURVEY 8d / north_star state the roofline as dense TF32 peak / 3 (3xTF32):
+                                 frac_vs_3xtf32_roofline=achieved / (pk["bf16"] / 2.0 / 3.0)),
                    clocks=clocks)
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline_sample(frames=2)

@@ -17,9 +17,34 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
   const int p0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* s = src + frame * frame_stride;
-  for (int c = warp; c < C; c += 8) {
-    int p = p0 + lane;
-    tile[c * 33 + lane] = (p < n_pix) ? __ldg(s + c * chan_stride + p) : 0.f;
+  // HBM-bound: keep many bytes in flight per thread.  Full, 16-byte aligned tiles are read as float4 (4 pixels of
+  // one channel per thread, 8 independent loads unrolled); ragged / misaligned ones element by element.
+  const bool vec = p0 + 32 <= n_pix && (chan_stride & 3) == 0 && (frame_stride & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec) {
+    const int quad = threadIdx.x & 7, c0 = threadIdx.x >> 3;       // 8 quads x 32 channels per pass
+    for (int cb = 0; cb < C; cb += 256) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cb + c0 + 32 * k;
+        v[k] = c < C ? __ldg(reinterpret_cast<const float4*>(s + c * chan_stride + p0) + quad)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cb + c0 + 32 * k;
+        if (c < C) {
+          float* t = tile + c * 33 + 4 * quad;
+          t[0] = v[k].x; t[1] = v[k].y; t[2] = v[k].z; t[3] = v[k].w;
+        }
+      }
+    }
+  } else {
+    for (int c = warp; c < C; c += 8) {
+      int p = p0 + lane;
+      tile[c * 33 + lane] = (p < n_pix) ? __ldg(s + c * chan_stride + p) : 0.f;
+    }
   }
   __syncthreads();
   // per-pixel L2 norm over C: warp w handles pixels w, w+8, ...

@@ -667,17 +667,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// exact fp32 value of <query row, key row idx> (all lanes return the same sum)
+// this lane's share of the exact fp32 value of <query row, key row>
 template <int NH2>
-__device__ __forceinline__ float exact_dot(const __half* __restrict__ bank, const float* xq, int slot, int pix,
-                                           int n_pix, int C, int lane) {
+__device__ __forceinline__ float partial_dot(const __half* __restrict__ bank, const float* xq, int slot, int pix,
+                                             int n_pix, int C, int lane) {
   const __half* hi = bank + ((int64_t)slot * 2 * n_pix + pix) * C;
   float xk[2 * NH2];
   load_row_f32<NH2>(hi, hi + (int64_t)n_pix * C, lane, xk);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 2 * NH2; ++i) s = fmaf(xq[i], xk[i], s);
-  return warp_sum(s);
+  return s;
+}
+// exact fp32 value of <query row, key row idx> (all lanes return the same sum)
+template <int NH2>
+__device__ __forceinline__ float exact_dot(const __half* __restrict__ bank, const float* xq, int slot, int pix,
+                                           int n_pix, int C, int lane) {
+  return warp_sum(partial_dot<NH2>(bank, xq, slot, pix, n_pix, C, lane));
 }
 
 constexpr int RS_WARPS = 8;
@@ -829,10 +835,19 @@ exact_scan_kernel(const __half* __restrict__ bank, const ScanParams p) {
       const int x_lo = masked ? max(0, qx - p.reach) : 0, x_hi = masked ? min(p.W - 1, qx + p.reach) : p.W - 1;
       for (int y = y_lo; y <= y_hi; ++y, ++rowctr) {
         if (rowctr % SC_WARPS != warp) continue;
-        for (int x = x_lo; x <= x_hi; ++x) {
-          if (masked && !in_mask(y - qy, x - qx, p.radius, p.mode)) continue;
-          const float v = exact_dot<NH2>(bank, xq, slot, y * p.W + x, p.n_pix, p.C, lane);
-          if (v > top.thr()) top.push(v, pos_base + y * p.W + x);
+        for (int x = x_lo; x <= x_hi; x += 4) {             // four keys in flight per warp (latency-bound otherwise)
+          float part[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ok[u] = x + u <= x_hi && (!masked || in_mask(y - qy, x + u - qx, p.radius, p.mode));
+            part[u] = ok[u] ? partial_dot<NH2>(bank, xq, slot, y * p.W + x + u, p.n_pix, p.C, lane) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float v = warp_sum(part[u]);
+            if (ok[u] && v > top.thr()) top.push(v, pos_base + y * p.W + x + u);
+          }
         }
       }
     }

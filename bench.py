@@ -281,6 +281,14 @@ def run_ours(args):
         if args.engine == "prefilter":
             kname = "affinity_prefilter_tc16_kernel + rescore_kernel + exact_scan_kernel (K1, experimental prefilter engine)"
         traffic, traffic_src = k1_traffic(split)
+        # dense pairs the engine multiplies: job-packed tiles for the fp16 engine (csrc/topk_tc16g.cu)
+        mode_id = _lib.MASK_CIRCLE
+        r = WORK["neighbor_range"] // 2
+        J = engine.pick_packing(clip.table, 0, len(clip.table), H, W, r, mode_id) if (split == "f16" and args.engine == "auto") else 1
+        if split == "f16":
+            dense = engine.dense_pairs(clip.table, 0, len(clip.table), H, W, r, mode_id, J)
+        else:
+            dense = dense_pairs(H, W, r, split) * work["mem_entries"]
         out = dict(metric="propagated frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                    warmup=n_warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype=("f16x3" if split == "f16" else "tf32x3") + " split, fp32 accumulate (fp32-faithful)",
@@ -298,9 +306,9 @@ def run_ours(args):
                                  flops_per_launch=work["flops_per_step"],
                                  # geometry: a 128-query tile multiplies the union of its queries' circles, in whole
                                  # key boxes.  frac_dense = what the tensor pipe itself sustains (dense MACs / peak)
-                                 tile_overhead=dense_pairs(H, W, WORK["neighbor_range"] // 2, split) / work["in_mask_pairs"],
-                                 frac_dense=achieved / peak * dense_pairs(H, W, WORK["neighbor_range"] // 2, split)
-                                 / work["in_mask_pairs"],
+                                 tile_overhead=dense / (work["in_mask_pairs"] * work["mem_entries"]),
+                                 frac_dense=achieved / peak * dense / (work["in_mask_pairs"] * work["mem_entries"]),
+                                 jobs_per_tile=J,
                                  # SURVEY 8d / north_star state the roofline as dense TF32 peak / 3 (3xTF32):
                                  frac_vs_3xtf32_roofline=achieved / (pk["bf16"] / 2.0 / 3.0)),
                    clocks=clocks)

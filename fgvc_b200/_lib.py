@@ -46,6 +46,8 @@ SIGNATURES = {
     "fgvc_affinity_topk_workspace_bytes": (L64, [I, I, I, I]),
     "fgvc_prefilter_supported": (I, [I, I, I, I, I, I]),
     "fgvc_affinity_topk_ws": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, I, P, L64, P]),
+    "fgvc_affinity_topk_packed": (I, [P, I, I, I, I, P, P, I, P, P, I, I, I, I, I, P, P, P]),
+    "fgvc_packed_tile_shape": (I, [I, I, I, I, I, P, P, P]),
     "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
     "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, I, P, I, P]),
     "fgvc_dense_propagate": (I, [P, I, I, I, I, P, I, P, P, I, I, F, I, P, I, P]),

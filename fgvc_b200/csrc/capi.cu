@@ -132,6 +132,33 @@ extern "C" int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format,
                             K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
 }
 
+extern "C" int fgvc_packed_tile_shape(int32_t H, int32_t W, int32_t radius, int32_t mask_mode, int32_t jobs_per_tile,
+                                      int32_t* tile_h, int32_t* tile_w, int32_t* box_h) {
+  FGVC_CHECK_ARG(tile_h && tile_w && box_h && H > 0 && W > 0 && radius >= 1, "fgvc_packed_tile_shape: bad arguments");
+  FGVC_CHECK_ARG(jobs_per_tile == 1 || jobs_per_tile == 2 || jobs_per_tile == 4, "fgvc_packed_tile_shape: jobs_per_tile");
+  int a, b, c;
+  packed_tile_shape(H, W, mask_reach(radius, mask_mode), jobs_per_tile, &a, &b, &c);
+  *tile_h = a; *tile_w = b; *box_h = c;
+  return FGVC_OK;
+}
+
+extern "C" int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                                         const fgvc_job* jobs, const fgvc_tile_group* tile_groups,
+                                         int32_t n_tile_groups, const int32_t* union_feat_slot, const int32_t* union_pos,
+                                         int32_t jobs_per_tile, int32_t radius, int32_t mask_mode, int32_t K,
+                                         int32_t groups, float* topk_val, int32_t* topk_idx, void* stream) {
+  FGVC_CHECK_ARG(feat_bank && jobs && tile_groups && union_feat_slot && union_pos && topk_val && topk_idx,
+                 "fgvc_affinity_topk_packed: null pointer");
+  FGVC_CHECK_ARG(H > 0 && W > 0 && n_tile_groups > 0 && n_slots > 0, "fgvc_affinity_topk_packed: bad shape");
+  FGVC_CHECK_ARG(tc16_supported(H, W, C, K), "fgvc_affinity_topk_packed: needs C %% 64 == 0, C <= 256, K <= 16 (C=%d K=%d)", C, K);
+  FGVC_CHECK_ARG(groups >= 1 && groups <= 64, "fgvc_affinity_topk_packed: groups=%d not in [1,64]", groups);
+  FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk_packed: radius=%d must be >= 1", radius);
+  FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk_packed: bad mask mode");
+  return launch_affinity_topk_tc16_packed(feat_bank, n_slots, H, W, C, jobs, tile_groups, n_tile_groups, union_feat_slot,
+                                          union_pos, jobs_per_tile, radius, mask_mode, K, groups, topk_val, topk_idx,
+                                          (cudaStream_t)stream);
+}
+
 extern "C" int fgvc_debug_affinity_boxes(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                                          const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
                                          int32_t radius, int32_t mask_mode, int32_t K, float* topk_val,

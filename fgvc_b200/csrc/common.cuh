@@ -166,6 +166,11 @@ int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, c
                         int Lp, void* ws, int64_t ws_bytes, cudaStream_t st);
 int launch_labels_to_nchw_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int Lp, int L,
                                int n_pix, float* maps_nchw, cudaStream_t st);
+void packed_tile_shape(int H, int W, int reach, int jobs_per_tile, int* QH, int* QW, int* BH);
+int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs,
+                                     const fgvc_tile_group* tgroups, int n_tgroups, const int32_t* uent,
+                                     const int32_t* upos, int jobs_per_tile, int radius, int mode, int K, int groups,
+                                     float* tv, int32_t* ti, cudaStream_t st);
 int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
                        int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st);
 int launch_labels_harden(float* lab_slot, int n_pix, int L, int Lp, cudaStream_t st);

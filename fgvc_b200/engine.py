@@ -104,6 +104,7 @@ class JobTable:
     def __init__(self):
         self.jobs, self.mem_feat, self.mem_label = [], [], []
         self._dev = None
+        self._packed = {}
 
     def add(self, q_slot, mem_feat_slots, mem_label_slots, out_slot, unmasked=0):
         """``unmasked``: number of leading memory entries without the radius mask
@@ -115,6 +116,7 @@ class JobTable:
         self.mem_label.extend(int(s) for s in mem_label_slots)
         self.jobs.append((int(q_slot), b, b + len(mem_feat_slots), int(out_slot)))
         self._dev = None
+        self._packed = {}
         return len(self.jobs) - 1
 
     def __len__(self):
@@ -134,6 +136,52 @@ class JobTable:
 
     def host_job(self, i):
         return Job(*self.jobs[i])
+
+    def union_sizes(self, j0, j1, J):
+        """sizes of the union memory lists when jobs [j0, j1) are packed J at a time (cost model)."""
+        out = []
+        for a in range(j0, j1, J):
+            keys = set()
+            for i in range(a, min(a + J, j1)):
+                seen = {}
+                for raw in self.mem_feat[self.jobs[i][1]:self.jobs[i][2]]:
+                    occ = seen.get(raw, 0)
+                    seen[raw] = occ + 1
+                    keys.add((raw, occ))
+            out.append(len(keys))
+        return out
+
+    def packed(self, j0, j1, J, device):
+        """Tile groups of J consecutive jobs of [j0, j1) for fgvc_affinity_topk_packed: (groups [n,8] int32,
+        union entries [U] int32, union positions [U,4] int32) on ``device``.  A memory list is a multiset (frame 0
+        twice while t <= precede_frames): the k-th occurrence of a frame in one job is matched with the k-th
+        occurrence in the others.  Union entries are ordered oldest frame first -- the kernel walks them backwards."""
+        key = (j0, j1, J, str(device))
+        hit = self._packed.get(key)
+        if hit is not None:
+            return hit
+        groups, uent, upos = [], [], []
+        for a in range(j0, j1, J):
+            members = list(range(a, min(a + J, j1)))
+            table = {}
+            for li, i in enumerate(members):
+                seen = {}
+                b, e = self.jobs[i][1], self.jobs[i][2]
+                for pos, raw in enumerate(self.mem_feat[b:e]):
+                    occ = seen.get(raw, 0)
+                    seen[raw] = occ + 1
+                    table.setdefault((raw, occ), [-1, -1, -1, -1])[li] = pos
+            order = sorted(table, key=lambda k: (k[0] & ~_lib.MEM_UNMASKED, 0 if (k[0] & _lib.MEM_UNMASKED) else 1, k[1]))
+            u0 = len(uent)
+            for k in order:
+                uent.append(k[0])
+                upos.append(table[k])
+            groups.append(members + [-1] * (4 - len(members)) + [len(members), u0, len(uent), 0])
+        out = (torch.tensor(groups, dtype=torch.int32).reshape(-1, 8).to(device),
+               torch.tensor(uent, dtype=torch.int32).to(device),
+               torch.tensor(upos, dtype=torch.int32).reshape(-1, 4).to(device))
+        self._packed[key] = out
+        return out
 
 
 def pick_groups(n_jobs, H, W, max_mem, max_groups=4):
@@ -232,6 +280,65 @@ def _workspace(dev, nbytes):
     return ws
 
 
+_COVER = {}
+
+
+def _cover_keys(H, W, radius, mode, J):
+    """Keys a query tile multiplies (whole key boxes of its radius halo that some query can see), summed over
+    the tiles of a map, for J jobs per tile -- the geometry of csrc/topk_tc16g.cu.  Every tile is a full M = 128
+    MMA, so the tensor work of a launch is  sum over tile groups of |union memory list| x this number."""
+    key = (H, W, radius, mode, J)
+    if key in _COVER:
+        return _COVER[key]
+    import ctypes as ct
+    qh, qw, bh = ct.c_int32(), ct.c_int32(), ct.c_int32()
+    call("fgvc_packed_tile_shape", H, W, int(radius), int(mode), int(J), ct.byref(qh), ct.byref(qw), ct.byref(bh))
+    QH, QW, BH = qh.value, qw.value, bh.value
+    reach = radius - 1 if mode == _lib.MASK_CIRCLE else radius
+
+    def seen(dy, dx):
+        return dy * dy + dx * dx < radius * radius if mode == _lib.MASK_CIRCLE else (dy <= radius and dx <= radius)
+
+    total = keys = 0
+    for qy0 in range(0, H, QH):
+        for qx0 in range(0, W, QW):
+            y_lo, y_hi = max(0, qy0 - reach), min(H - 1, qy0 + QH - 1 + reach)
+            x_lo, x_hi = max(0, qx0 - reach), min(W - 1, qx0 + QW - 1 + reach)
+            qy1, qx1 = min(H - 1, qy0 + QH - 1), min(W - 1, qx0 + QW - 1)
+            for by in range(y_lo, y_hi + 1, BH):
+                dy = max(0, by - qy1, qy0 - min(H - 1, by + BH - 1))
+                for bx in range(x_lo, x_hi + 1, 16):
+                    dx = max(0, bx - qx1, qx0 - min(W - 1, bx + 15))
+                    if seen(dy, dx):
+                        total += 16 * BH + 24          # + the fixed per-box hand-shake (box_cost16)
+                        keys += 16 * BH
+    _COVER[key] = total
+    _COVER[key + ("keys",)] = keys
+    return total
+
+
+def dense_pairs(table, j0, j1, H, W, radius, mode, J):
+    """(query row, key) pairs the tensor engine multiplies for jobs [j0, j1) packed J per tile: every tile is a
+    full M = 128 MMA against every key box of its halo, for every entry of the group's union memory list."""
+    _cover_keys(H, W, radius, mode, J)
+    return 128 * _COVER[(H, W, radius, mode, J, "keys")] * sum(table.union_sizes(j0, j1, J))
+
+
+def pick_packing(table, j0, j1, H, W, radius, mode):
+    """jobs per tile (1, 2 or 4) with the least tensor work for jobs [j0, j1); FGVC_PACK forces it."""
+    forced = os.environ.get("FGVC_PACK")
+    if forced is not None:
+        return int(forced)
+    if j1 - j0 < 2:
+        return 1
+    best, best_cost = 1, None
+    for J in (1, 2, 4):
+        cost = sum(table.union_sizes(j0, j1, J)) * _cover_keys(H, W, radius, mode, J)
+        if best_cost is None or cost < 0.97 * best_cost:      # packing must pay for its extra set-up
+            best, best_cost = J, cost
+    return best
+
+
 def chain_workspace(dev, n_jobs, n_pix, K, flags=0):
     """(pointer, bytes) of the scratch that lets a clip tail run its gather chain as one persistent kernel;
     (None, 0) = per-frame launches (hard propagation decodes between frames, single-frame ranges gain nothing)."""
@@ -260,6 +367,16 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
+    # fp16 tensor engine: pack J consecutive jobs into one query tile when that saves tensor work (topk_tc16g.cu)
+    if engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05) and bank.fmt == _lib.BANK_F16 and \
+            _lib.load().fgvc_tc_supported(bank.fmt, bank.H, bank.W, bank.C, int(K)):
+        J = pick_packing(table, j0, j1, bank.H, bank.W, int(radius), mode)
+        if J > 1:
+            tg, uent, upos = table.packed(j0, j1, J, dev)
+            call("fgvc_affinity_topk_packed", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C, ptr(jobs), ptr(tg),
+                 int(tg.shape[0]), ptr(uent), ptr(upos), int(J), int(radius), mode, int(K), int(groups),
+                 ptr(lists.val), ptr(lists.idx), stream_ptr())
+            return lists
     ws, ws_bytes = None, 0
     if engine == _lib.ENGINE_PREFILTER and bank.unit_rows and \
             _lib.load().fgvc_prefilter_supported(bank.fmt, bank.H, bank.W, bank.C, int(K), int(groups)):

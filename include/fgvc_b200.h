@@ -89,6 +89,19 @@ typedef struct fgvc_job {
   int32_t out_slot;   /* label-bank slot written by fgvc_gather_labels */
 } fgvc_job;
 
+/* Job-packed query tiles of the fp16 tensor engine (fgvc_affinity_topk_packed): a tile group = up to 4 jobs that
+ * share most of their memory frames (consecutive query frames of a clip) and are multiplied against each key box
+ * together.  Memory entries [u_begin, u_end) of the union tables list every (frame, mask flag) any job of the group
+ * uses; union_pos[entry][i] is the entry's position in job[i]'s own memory list (what the top-k indices refer to)
+ * or -1 when job[i] does not have it. */
+typedef struct fgvc_tile_group {
+  int32_t job[4];   /* indices into jobs[]; unused = -1 */
+  int32_t n_jobs;
+  int32_t u_begin;
+  int32_t u_end;
+  int32_t reserved;
+} fgvc_tile_group;
+
 /* fgvc_gather_labels flags */
 #define FGVC_WEIGHT_COSINE 1 /* weights = clamp(a, 0)^2 instead of softmax(a)   (mode='cosine', local_attention.py:371) */
 #define FGVC_HARD_PROP 4     /* clip tails only: the memory keeps one_hot(argmax) of each propagated frame
@@ -154,6 +167,18 @@ FGVC_API int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, i
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, int32_t unit_rows,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K1 on job-packed tiles (F16 bank, tcgen05 fp16 three-term engine only): same output as fgvc_affinity_topk
+ * for the jobs named by the tile groups (lists are written at [job][group][Nq][K] by job index).  jobs_per_tile in
+ * {1, 2, 4}: 128 tile rows = jobs_per_tile jobs x 128 / jobs_per_tile pixels (16x8 | 8x8 | 8x4 block).
+ * fgvc_packed_tile_shape reports the pixel block and key-box height the launcher will use (for costing). */
+FGVC_API int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                       const fgvc_job* jobs, const fgvc_tile_group* tile_groups, int32_t n_tile_groups,
+                       const int32_t* union_feat_slot, const int32_t* union_pos, int32_t jobs_per_tile,
+                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
+                       float* topk_val, int32_t* topk_idx, void* stream);
+FGVC_API int fgvc_packed_tile_shape(int32_t H, int32_t W, int32_t radius, int32_t mask_mode, int32_t jobs_per_tile,
+                       int32_t* tile_h, int32_t* tile_w, int32_t* box_h);
 
 /* test hook (tcgen05 engine, groups = 1, use with ONE query tile): additionally dumps the
  * raw 128 x 128 accumulator tile of the first dbg_max_boxes key boxes to

@@ -563,6 +563,28 @@ def test_clip_host_pipeline_equals_resident_run():
     assert float((err > TOL).float().mean()) <= 2e-3
 
 
+def test_gather_chain_equals_per_frame_launches(monkeypatch):
+    """The persistent gather chain (one cooperative kernel, grid barrier per frame, gather.cu) must give the
+    same label maps and masks, bit for bit, as one K1b launch per frame -- short rows (L = 5) and long rows
+    (L = 70: several float4 per query, more CTAs than queries / 32)."""
+    from fgvc_b200 import engine
+    g = torch.Generator().manual_seed(12)
+    for L in (5, 70):
+        T, C, H, W = 9, 64, 22, 26
+        feats = _coherent(g, T, C, H, W).cuda()
+        first = torch.rand(L, H, W, generator=g).cuda()
+        cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=10, with_first=True,
+                   with_first_neighbor=True)
+        clip = engine.MaskClipPropagator(T, C, H, W, L, (44, 52), cfg, torch.device("cuda"))
+        monkeypatch.delenv("FGVC_NO_CHAIN", raising=False)
+        maps, masks = clip.run(feats, first)
+        maps, masks = maps.clone(), masks.clone()
+        monkeypatch.setenv("FGVC_NO_CHAIN", "1")
+        maps2, masks2 = clip.run(feats, first)
+        assert torch.equal(maps, maps2) and torch.equal(masks, masks2)
+    monkeypatch.delenv("FGVC_NO_CHAIN", raising=False)
+
+
 @pytest.mark.parametrize("engine", ["simt", "tc16"])
 @pytest.mark.parametrize("mode,sim_mode", [("cosine", "dot_product"), ("softmax", "l2-distance"), ("cosine", "l2-distance")])
 def test_weight_and_similarity_variants(mode, sim_mode, engine):

@@ -21,6 +21,10 @@ CFGS = {
     "cfg3": dict(hw=(256, 256), T=50, P=256, nr=30, precede=5),
     "cfg4": dict(hw=(320, 320), T=32, P=15, nr=30, precede=5),
     "cfg5s": dict(hw=(256, 256), T=250, P=128, nr=30, precede=5),
+    # BASELINE config 5 memory-length sweep (same 1/8 point shard)
+    "cfg5s_p10": dict(hw=(256, 256), T=250, P=128, nr=30, precede=10),
+    "cfg5s_p20": dict(hw=(256, 256), T=250, P=128, nr=30, precede=20),
+    "cfg5s_p40": dict(hw=(256, 256), T=250, P=128, nr=30, precede=40),
 }
 
 

@@ -276,10 +276,6 @@ def run_ours(args):
         achieved = work["flops_per_step"] / (k1 / 1e3) / 1e12
         # three tensor MACs per fp32-faithful MAC; the tf32 pipe runs at half the 16-bit rate
         peak = pk["bf16"] / 3.0 if split == "f16" else pk["bf16"] / 2.0 / 3.0
-        kname = "affinity_topk_tc16_kernel (K1, fp16 three-term split)" if split == "f16" else \
-            "affinity_topk_tc_kernel (K1, 3xTF32)"
-        if args.engine == "prefilter":
-            kname = "affinity_prefilter_tc16_kernel + rescore_kernel + exact_scan_kernel (K1, experimental prefilter engine)"
         traffic, traffic_src = k1_traffic(split)
         # dense pairs the engine multiplies: job-packed tiles for the fp16 engine (csrc/topk_tc16g.cu)
         mode_id = _lib.MASK_CIRCLE
@@ -289,6 +285,12 @@ def run_ours(args):
             dense = engine.dense_pairs(clip.table, 0, len(clip.table), H, W, r, mode_id, J)
         else:
             dense = dense_pairs(H, W, r, split) * work["mem_entries"]
+        kname = "affinity_topk_tc16_kernel (K1, fp16 three-term split)" if split == "f16" else \
+            "affinity_topk_tc_kernel (K1, 3xTF32)"
+        if split == "f16" and args.engine == "auto" and J > 1:
+            kname = f"affinity_topk_tc16g_kernel (K1, fp16 three-term split, {J} jobs packed per query tile)"
+        if args.engine == "prefilter":
+            kname = "affinity_prefilter_tc16_kernel + rescore_kernel + exact_scan_kernel (K1, experimental prefilter engine)"
         out = dict(metric="propagated frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                    warmup=n_warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype=("f16x3" if split == "f16" else "tf32x3") + " split, fp32 accumulate (fp32-faithful)",

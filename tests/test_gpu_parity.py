@@ -563,6 +563,61 @@ def test_clip_host_pipeline_equals_resident_run():
     assert float((err > TOL).float().mean()) <= 2e-3
 
 
+@pytest.mark.parametrize("geom", [(26, 37, 64, 10, 14, 6), (24, 40, 256, 12, 9, 3)])
+def test_job_packed_tiles_equal_unpacked(monkeypatch, geom):
+    """csrc/topk_tc16g.cu: J = 2 / 4 consecutive query frames per M = 128 tile must give the same top-k lists as
+    one job per tile -- values bit for bit (same MMA sequence per (query, key) pair), indices up to the order of
+    exactly tied values (frame 0 twice in the memory)."""
+    from fgvc_b200 import engine, _lib
+    H, W, C, T, precede, r = geom
+    g = torch.Generator().manual_seed(H)
+    feats = _coherent(g, T, C, H, W).cuda()
+    bank = engine.FeatureBank(T, C, H, W, torch.device("cuda"), split="f16")
+    bank.load_frames(feats, 0)
+    tb = engine.JobTable()
+    for t in range(1, T):
+        mem = engine.memory_frames(t, precede, True)
+        tb.add(t, mem, mem, t, unmasked=1 if t % 3 == 0 else 0)       # some jobs with an unmasked first frame
+    labels = engine.LabelBank(T, 5, H, W, torch.device("cuda"))
+    first = torch.rand(5, H, W, generator=g).cuda()
+    out, prop = {}, {}
+    for J in (1, 2, 4):
+        monkeypatch.setenv("FGVC_PACK", str(J))
+        lists = engine.affinity_topk(bank, tb, r, 10, groups=1, engine=_lib.ENGINE_TCGEN05)
+        torch.cuda.synchronize()
+        out[J] = (lists.val.clone(), lists.idx.clone())
+        # with the memory split into groups the per-group lists differ by construction (the UNION list is what is
+        # split); what must agree is the merged result, i.e. the propagated labels
+        lists2 = engine.affinity_topk(bank, tb, r, 10, groups=3, engine=_lib.ENGINE_TCGEN05)
+        labels.put_nchw(first, 0)
+        for j in range(len(tb)):
+            engine.gather_labels(lists2, tb, j, j + 1, labels, 0.07)
+        prop[J] = labels.buf.clone()
+    monkeypatch.delenv("FGVC_PACK", raising=False)
+    for J in (2, 4):
+        assert torch.equal(out[J][0], out[1][0]), J
+        same = out[J][1] == out[1][1]
+        # where indices differ the values must be exactly tied with a neighbour in the list
+        v = out[1][0]
+        tied = torch.zeros_like(same)
+        tied[..., 1:] |= v[..., 1:] == v[..., :-1]
+        tied[..., :-1] |= v[..., :-1] == v[..., 1:]
+        # ... or sit on the list boundary: the k-th and (k+1)-th candidates are the same key through the two
+        # entries of frame 0 -- then both engines hold the same (frame, pixel), reached through another position
+        def keys(idx):
+            n_pix = H * W
+            pos, pix = torch.div(idx.clamp_min(0), n_pix, rounding_mode="floor"), idx.clamp_min(0) % n_pix
+            slot = torch.zeros_like(idx)
+            for j in range(len(tb)):
+                mem = torch.tensor(tb.mem_feat[tb.jobs[j][1]:tb.jobs[j][2]], device=idx.device) & ~_lib.MEM_UNMASKED
+                slot[j] = mem[pos[j].clamp_max(mem.numel() - 1).long()].to(idx.dtype)
+            return slot * n_pix + pix
+        same_key = keys(out[J][1]) == keys(out[1][1])
+        assert bool((same | tied | same_key).all()), J
+        assert float(same.float().mean()) > 0.95          # the rest: swapped exact ties of the doubled frame 0
+        assert (prop[J] - prop[1]).abs().max() < 1e-6, J
+
+
 def test_gather_chain_equals_per_frame_launches(monkeypatch):
     """The persistent gather chain (one cooperative kernel, grid barrier per frame, gather.cu) must give the
     same label maps and masks, bit for bit, as one K1b launch per frame -- short rows (L = 5) and long rows

@@ -37,6 +37,38 @@ def test_job_table_layout():
     assert j.dtype == torch.int32 and j.shape == (2, 4) and mf.shape == (5,)
 
 
+def test_job_packing_tables_reproduce_every_memory_list():
+    """JobTable.packed (host side of csrc/topk_tc16g.cu): the union list of a tile group, read through union_pos,
+    must give back every job's own memory multiset in its own order -- incl. frame 0 twice while t <= precede."""
+    for precede, T, unmasked in ((3, 9, 0), (20, 30, 1), (5, 7, 0)):
+        tb = engine.JobTable()
+        for t in range(1, T):
+            mem = engine.memory_frames(t, precede, True)
+            tb.add(t, mem, mem, t, unmasked=unmasked)
+        for J in (1, 2, 4):
+            tg, uent, upos = tb.packed(0, len(tb), J, "cpu")
+            assert tg.shape == (-(-len(tb) // J), 8) and upos.shape == (uent.numel(), 4)
+            seen_jobs = []
+            for g in tg.tolist():
+                members, n, u0, u1 = g[:4], g[4], g[5], g[6]
+                assert members[n:] == [-1] * (4 - n) and 1 <= n <= J
+                # oldest frame first (the kernel walks the list backwards: newest first)
+                slots = [int(x) & ~0x40000000 for x in uent[u0:u1].tolist()]
+                assert slots == sorted(slots)
+                for li in range(n):
+                    job = members[li]
+                    seen_jobs.append(job)
+                    b, e = tb.jobs[job][1], tb.jobs[job][2]
+                    got = sorted((int(upos[u, li]), int(uent[u])) for u in range(u0, u1) if int(upos[u, li]) >= 0)
+                    assert [p for p, _ in got] == list(range(e - b))          # every position exactly once
+                    assert [r for _, r in got] == tb.mem_feat[b:e]
+                for li in range(n, 4):
+                    assert (upos[u0:u1, li] == -1).all()
+            assert seen_jobs == list(range(len(tb)))
+            assert tb.union_sizes(0, len(tb), J) == [g[6] - g[5] for g in tg.tolist()]
+    # long memories pack, short ones do not (cost model over the exact box counts needs the library: skipped here)
+
+
 def test_pick_groups_fills_the_chip():
     assert engine.pick_groups(1, 60, 107, 21) >= 2          # one DAVIS frame: split the memory
     assert engine.pick_groups(63, 60, 107, 21) == 1         # a whole clip: 3528 CTAs = 23.8 waves already

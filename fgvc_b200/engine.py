@@ -520,17 +520,19 @@ class MaskClipPropagator:
             self.flags |= _lib.HARD_PROP
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 
-    def _decode(self, t):
+    def _decode(self, t, masks=None):
+        masks = self.masks if masks is None else masks
         call("fgvc_decode_masks_pixmajor", ptr(self.labels.buf), t, self.labels.Lp, self.L, self.H, self.W,
-             self.out_hw[0], self.out_hw[1], ptr(self.scratch), ptr(self.masks[t]), stream_ptr())
+             self.out_hw[0], self.out_hw[1], ptr(self.scratch), ptr(masks[t]), stream_ptr())
 
-    def _tail(self, j0, j1, want_maps, lists=None):
+    def _tail(self, j0, j1, want_maps, lists=None, masks=None):
         lists = lists or self.lists
+        masks = self.masks if masks is None else masks
         jobs, _, mem_label = self.table.device(self.device)
         call("fgvc_mask_clip_tail", ptr(lists.val), ptr(lists.idx), lists.K, lists.groups,
              ptr(jobs), ptr(self.jobs_host), j0, j1, ptr(mem_label), self.H, self.W,
              self.temperature, self.flags, ptr(self.labels.buf), self.labels.Lp, self.L, self.out_hw[0],
-             self.out_hw[1], ptr(self.scratch), ptr(self.masks), ptr(self.maps) if want_maps else None,
+             self.out_hw[1], ptr(self.scratch), ptr(masks), ptr(self.maps) if want_maps else None,
              *chain_workspace(self.device, j1 - j0, self.H * self.W, lists.K, self.flags), stream_ptr())
 
     def _k1(self, j0, j1, lists=None):
@@ -581,46 +583,77 @@ class MaskClipPropagator:
 
     def run_host(self, feats_host, onehot_host, masks_host, chunks=None):
         """End-to-end form: PINNED host features [T,C,H,W] / one-hot [L,H,W] in, uint8 masks
-        [T,h,w] out to pinned host memory.  The host->device copy of job chunk i+1 (copy stream)
-        overlaps K0 + K1 + tail of chunk i: a frame's jobs only need earlier frames.  ``chunks``:
-        list of (job_begin, job_end); default = :func:`plan_chunks` (full last waves)."""
+        [T,h,w] out to pinned host memory.  Two levels of overlap, nothing synchronises the host:
+          * within a clip the host->device copy of job chunk i+1 (copy stream) overlaps K0 + K1 + tail of chunk
+            i -- a frame's jobs only need earlier frames.  ``chunks``: list of (job_begin, job_end); default =
+            :func:`plan_chunks` (best latency of ONE clip);
+          * across clips the staging buffers are double-buffered, so the copies of the NEXT call start while this
+            call still computes (they only wait for the K0 launches that read the same staging buffer two calls
+            ago).  For a stream of clips ``chunks=[(0, n_jobs)]`` is then the fastest plan: the copies are
+            hidden behind the previous clip and K1 runs as one launch."""
         cfg = self.cfg
         if not hasattr(self, "_stage"):
-            self._stage = torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
-            self._onehot = torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
+            self._stage = [torch.empty(self.T, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
+                           for _ in range(2)]
+            self._onehot = [torch.empty(self.L, self.H, self.W, dtype=torch.float32, device=self.device)
+                            for _ in range(2)]
+            self._stage_free = [None, None]                         # last K0 that read the buffer
+            self._masks2 = [self.masks, torch.empty_like(self.masks)]   # device masks, one per call in flight
+            self._masks_free = [None, None]                         # last device->host copy that read the buffer
+            self._flip = 0
             self._copy = torch.cuda.Stream(device=self.device)
             self._back = torch.cuda.Stream(device=self.device)      # device->host copies of finished masks
             self._chunks = plan_chunks(len(self.table), (-(-self.H // 8)) * (-(-self.W // 16))) if self.T > 1 else []
         chunks = chunks or self._chunks
         cur = torch.cuda.current_stream()
-        self._copy.wait_stream(cur)                       # staging buffers free again
-        self._back.wait_stream(cur)
+        b = self._flip
+        self._flip ^= 1
+        stage, onehot, masks_dev = self._stage[b], self._onehot[b], self._masks2[b]
+        if self._masks_free[b] is not None:
+            cur.wait_event(self._masks_free[b])           # (two calls ago: long done)
+        if self._stage_free[b] is not None:
+            self._copy.wait_event(self._stage_free[b])    # staging buffer b free again
+        else:
+            self._copy.wait_stream(cur)
         evs = []
         with torch.cuda.stream(self._copy):
-            self._onehot.copy_(onehot_host, non_blocking=True)
+            onehot.copy_(onehot_host, non_blocking=True)
             f0 = 0
             for (j0, j1) in (chunks or [(0, 0)]):
                 f1 = j1 + 1 if j1 > j0 else self.T          # job j propagates frame j + 1
-                self._stage[f0:f1].copy_(feats_host[f0:f1], non_blocking=True)
+                stage[f0:f1].copy_(feats_host[f0:f1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy)
                 evs.append((f0, f1, j0, j1, ev))
                 f0 = f1
-        for f0, f1, j0, j1, ev in evs:
+        for n, (f0, f1, j0, j1, ev) in enumerate(evs):
             cur.wait_event(ev)
-            self.bank.load_frames(self._stage[f0:f1], f0, normalize=cfg.get("with_norm", True))
+            self.bank.load_frames(stage[f0:f1], f0, normalize=cfg.get("with_norm", True))
             if f0 == 0:
-                self.labels.put_nchw(self._onehot, 0)
-                self._decode(0)
+                self.labels.put_nchw(onehot, 0)
+                self._decode(0, masks_dev)
+            if n == len(evs) - 1:
+                free = torch.cuda.Event()
+                free.record(cur)
+                self._stage_free[b] = free
             if j1 > j0:
                 self._k1(j0, j1)
-                self._tail(j0, j1, False)
-            # ship the masks of this chunk while the next chunk computes (PCIe is full duplex)
+                self._tail(j0, j1, False, masks=masks_dev)
+            # ship the masks of this chunk while the next chunk / the next clip computes (PCIe is full duplex)
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(self._back):
                 self._back.wait_event(done)
                 m0 = 0 if f0 == 0 else f0
-                masks_host[m0:f1].copy_(self.masks[m0:f1], non_blocking=True)
-        cur.wait_stream(self._back)
+                masks_host[m0:f1].copy_(masks_dev[m0:f1], non_blocking=True)
+                if n == len(evs) - 1:
+                    mf = torch.cuda.Event()
+                    mf.record(self._back)
+                    self._masks_free[b] = mf
         return masks_host
+
+    def join_host(self):
+        """Make the current stream wait for the device->host copies of every ``run_host`` call so far (the
+        caller synchronises that stream, or the device, before reading ``masks_host``)."""
+        if hasattr(self, "_back"):
+            torch.cuda.current_stream().wait_stream(self._back)

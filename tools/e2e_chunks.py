@@ -13,9 +13,9 @@ clip = engine.MaskClipPropagator(T, W["channels"], H, Wd, W["objects"], W["image
 fh, oh = feats.cpu().pin_memory(), onehot.cpu().pin_memory()
 mh = torch.empty(tuple(clip.masks.shape), dtype=torch.uint8).pin_memory()
 tiles = (-(-H // 8)) * (-(-Wd // 16))
-plans = {"default": None}
-for cr in (0.6, 0.75, 0.85, 1.0, 1.2):
-    for lc in (0.4, 1.0, 2.0):
+plans = {"default": None, "whole": [(0, T - 1)]}
+for cr in (0.75, 1.2):
+    for lc in (0.4, 2.0):
         plans[f"cr{cr}_lc{lc}"] = engine.plan_chunks(T - 1, tiles, copy_ratio=cr, launch_cost=lc)
 for n in (2, 3, 4, 6, 8):
     step = -(-(T - 1) // n)
@@ -28,6 +28,7 @@ for name, ch in plans.items():
     e0.record()
     for _ in range(5):
         clip.run_host(fh, oh, mh, chunks=ch)
+    clip.join_host()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5

@@ -331,11 +331,15 @@ def pick_packing(table, j0, j1, H, W, radius, mode):
         return int(forced)
     if j1 - j0 < 2:
         return 1
+    ckey = ("pick", j0, j1, H, W, radius, mode)
+    if ckey in table._packed:
+        return table._packed[ckey]
     best, best_cost = 1, None
     for J in (1, 2, 4):
         cost = sum(table.union_sizes(j0, j1, J)) * _cover_keys(H, W, radius, mode, J)
         if best_cost is None or cost < 0.97 * best_cost:      # packing must pay for its extra set-up
             best, best_cost = J, cost
+    table._packed[ckey] = best
     return best
 
 

@@ -569,8 +569,12 @@ affinity_prefilter_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const
           bits1 = ky1 < p.H ? rowbits : 0u;
         }
         bool changed = false;
+        int rounds_before = st_rounds;
         if (do0) { ++st_rows; changed |= scan_row<KP>(top, r0, bits0, pos_base + ky0 * p.W + bx, floor_q, qvalid, st_rounds, st_ins); }
+        st_hot += st_rounds > rounds_before ? 1 : 0;
+        rounds_before = st_rounds;
         if (do1) { ++st_rows; changed |= scan_row<KP>(top, r1, bits1, pos_base + ky1 * p.W + bx, floor_q, qvalid, st_rounds, st_ins); }
+        st_hot += st_rounds > rounds_before ? 1 : 0;
         if (changed) s_run[wg * 128 + m] = (SH == 0 ? top.t0 : (SH == 2 ? top.t2 : top.t3));
       }
     });

@@ -475,14 +475,15 @@ def c2f_propagate(coarse, fine, table, job_index, fine_labels, radius, radius_fi
     n_mem = hj.mem_end - hj.mem_begin
     nq = coarse.H * coarse.W
     out = torch.empty(nq, fine_labels.Lp, dtype=torch.float32, device=dev)
-    sv = torch.empty(n_mem * nq, dtype=torch.float32, device=dev)
-    si = torch.empty(n_mem * nq, dtype=torch.int32, device=dev)
+    n_scr = int(_lib.load().fgvc_c2f_scratch_elems(n_mem, nq))
+    sv = torch.empty(n_scr, dtype=torch.float32, device=dev)
+    si = torch.empty(n_scr, dtype=torch.int32, device=dev)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     jptr = ctypes.c_void_p(jobs.data_ptr() + 16 * job_index)
     assert coarse.fmt == fine.fmt
     call("fgvc_c2f_propagate", ptr(coarse.buf), coarse.fmt, coarse.n_slots, coarse.H, coarse.W, coarse.C, ptr(fine.buf), fine.H, fine.W, fine.C,
          jptr, ctypes.byref(hj), ptr(mem_feat), ptr(mem_label), int(radius), mode, int(radius_fine), int(K),
-         float(temperature), ptr(fine_labels.buf), fine_labels.Lp, ptr(out), ptr(sv), ptr(si), int(engine),
+         float(temperature), ptr(fine_labels.buf), fine_labels.Lp, ptr(out), ptr(sv), ptr(si), n_scr, int(engine),
          stream_ptr())
     return out
 

@@ -257,14 +257,17 @@ FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx
  * scale*(ky,kx), zero padded (padded candidates: affinity 0, value 0), top-K over
  * T*R^2, softmax, gather of FINE labels.  Output on the coarse grid: out[Hc*Wc][Lp].
  * job_dev / job_host: the same job in device memory (read by K1) and host memory (read by
- * the launcher); scratch_val / scratch_idx: n_mem * Hc*Wc elements each. */
+ * the launcher); scratch_val / scratch_idx: fgvc_c2f_scratch_elems(n_mem, Hc*Wc) elements each (the coarse per-frame
+ * arg-max table, then the fine top-K lists).  With an F16 fine bank (Cf % 64 == 0, Cf <= 256, n_mem <= 32) the fine
+ * stage runs on the tensor cores as a window-mode K1 (csrc/topk_tc16w.cu); otherwise one warp per candidate. */
+FGVC_API int64_t fgvc_c2f_scratch_elems(int32_t n_mem, int32_t n_coarse);
 FGVC_API int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, int32_t n_slots, int32_t Hc, int32_t Wc,
                        int32_t C, const void* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,
                        const fgvc_job* job_dev, const fgvc_job* job_host,
                        const int32_t* mem_feat_slot, const int32_t* mem_label_slot, int32_t radius,
                        int32_t mask_mode, int32_t radius_fine, int32_t K, float temperature,
                        const float* fine_lab_bank, int32_t Lp, float* out, float* scratch_val,
-                       int32_t* scratch_idx, int32_t engine, void* stream);
+                       int32_t* scratch_idx, int64_t scratch_elems, int32_t engine, void* stream);
 
 #ifdef __cplusplus
 }

@@ -425,6 +425,36 @@ def test_c2f_matches_reference_golden(golden_dir, engine):
     assert float(err.median()) < TIGHT
 
 
+@pytest.mark.parametrize("geom", [(6, 7, 4, 64, 64, 3, 5, 5), (9, 20, 4, 64, 128, 2, 6, 12), (5, 5, 2, 128, 64, 4, 3, 2)])
+def test_c2f_window_engine_matches_oracle(monkeypatch, geom):
+    """Fine stage on the tensor cores (csrc/topk_tc16w.cu: window-mode K1 + tail) against the oracle restatement
+    of masked_attention_efficient_c2f (itself pinned to the genuine function by the CPU golden test) and against the
+    one-warp-per-candidate kernel.  Small maps with a big radius_fine put most windows across the border, where the
+    zero-padded positions (affinity 0, value 0) compete for the top-k."""
+    import fgvc_b200
+    Hc, Wc, s, C, Cf, T, L, rf = geom
+    g = torch.Generator().manual_seed(Hc * 100 + Wc)
+    f = _coherent(g, T + 1, C, Hc, Wc)
+    ff = _coherent(g, T + 1, Cf, Hc * s, Wc * s)
+    q, k = f[T][None], f[:T].permute(1, 0, 2, 3)[None].contiguous()
+    qf, kf = ff[T][None], ff[:T].permute(1, 0, 2, 3)[None].contiguous()
+    v = torch.rand(1, L, T, Hc * s, Wc * s, generator=g)
+    nr = 6
+    mask = fgvc_b200.spatial_neighbor(1, Hc, Wc, nr, "cuda", torch.float32)
+    args = [x.cuda() for x in (q, k, qf, kf, v)]
+    monkeypatch.delenv("FGVC_C2F_SIMT", raising=False)
+    got = fgvc_b200.masked_attention_efficient_c2f(*args, mask, temperature=0.07, topk=10, radius_fine=rf, split="f16")
+    monkeypatch.setenv("FGVC_C2F_SIMT", "1")
+    simt = fgvc_b200.masked_attention_efficient_c2f(*args, mask, temperature=0.07, topk=10, radius_fine=rf, split="f16")
+    monkeypatch.delenv("FGVC_C2F_SIMT", raising=False)
+    want = O.c2f_port(q, k, qf, kf, v, O.neighbor_mask(Hc, Wc, nr), temperature=0.07, topk=10, radius_fine=rf)["out"]
+    err = (got.cpu() - want).abs().amax(dim=1).flatten()
+    assert float((err > TOL).float().mean()) <= 0.03, float(err.max())      # near-ties of the coarse arg-max
+    assert float(err.median()) < TIGHT
+    err2 = (got - simt).abs().amax(dim=1).flatten()
+    assert float((err2 > TOL).float().mean()) <= 0.01 and float(err2.median()) < 1e-6
+
+
 # ---------------------------------------------------------------------- tracker driver
 @pytest.mark.parametrize("tag", ["s8", "s2"])
 def test_tracker_matches_reference_golden(golden_dir, tag):

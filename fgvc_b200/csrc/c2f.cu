@@ -114,6 +114,8 @@ c2f_fine_kernel(const void* __restrict__ fine_bank, int Hc, int Wc, int Hf, int 
   }
 }
 
+constexpr int C2F_TAIL_QB = 8;      // coarse queries per CTA: a coarse grid is small, keep the grid wide
+
 // Tail of the tensor-core fine stage (topk_tc16w.cu): per coarse query, the K best in-window fine keys are in
 // tv / ti.  The reference's windows are zero padded (F.unfold(padding = rf), local_attention.py:790-793): every
 // window position outside the fine map is a candidate too, with affinity 0 and value 0 -- their number is
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256)
 c2f_tail_kernel(const float* __restrict__ tv, const int32_t* __restrict__ ti, int k_in, int n_lists, int Hc, int Wc, int Hf, int Wf,
                 int scale, fgvc_job job, const int32_t* __restrict__ mem_label, const int32_t* __restrict__ best_idx,
                 int rf, float temperature, const float* __restrict__ fine_lab, int Lp, float* __restrict__ out) {
-  constexpr int QB = 64;
+  constexpr int QB = C2F_TAIL_QB;
   __shared__ float sw[QB][K];
   __shared__ int srow[QB][K];
   const int q0 = blockIdx.x * QB;
@@ -204,7 +206,7 @@ template <int K>
 static int launch_tail(const float* tv, const int32_t* ti, int k_in, int n_lists, int Hc, int Wc, int Hf, int Wf, int scale,
                        const fgvc_job& job, const int32_t* mem_label, const int32_t* best, int rf, float temperature,
                        const float* fine_lab, int Lp, float* out, cudaStream_t st) {
-  c2f_tail_kernel<K><<<cdiv(Hc * Wc, 64), 256, 0, st>>>(tv, ti, k_in, n_lists, Hc, Wc, Hf, Wf, scale, job, mem_label, best,
+  c2f_tail_kernel<K><<<cdiv(Hc * Wc, C2F_TAIL_QB), 256, 0, st>>>(tv, ti, k_in, n_lists, Hc, Wc, Hf, Wf, scale, job, mem_label, best,
                                                        rf, temperature, fine_lab, Lp, out);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;

@@ -479,6 +479,8 @@ int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W
   p.H = H; p.W = W; p.C = C; p.n_pix = H * W;
   p.radius = radius; p.mode = mode; p.reach = mask_reach(radius, mode);
   packed_tile_shape(H, W, p.reach, jobs_per_tile, &p.QH, &p.QW, &p.BH);
+  static const int force_bh = getenv("FGVC_TC16_BH") ? atoi(getenv("FGVC_TC16_BH")) : 0;   // timing experiments only
+  if (force_bh >= 1 && force_bh <= T16_MAX_BH) p.BH = force_bh;
   p.qw_shift = p.QW == 16 ? 4 : (p.QW == 8 ? 3 : 2);
   p.lpj_shift = jobs_per_tile == 1 ? 7 : (jobs_per_tile == 2 ? 6 : 5);
   p.groups = groups; p.k_out = K;

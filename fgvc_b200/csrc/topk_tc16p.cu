@@ -1,4 +1,6 @@
-// K1 (tcgen05 engine, fp16 PREFILTER + exact rescoring): the fast path of the F16 bank.
+// K1 (tcgen05 engine, fp16 PREFILTER + exact rescoring): EXPERIMENTAL engine of the F16 bank, explicit only
+// (FGVC_ENGINE_PREFILTER).  Same results as the exact engines; measured on B200 it is bound by the instruction
+// issue of its epilogue, not by the tensor pipe, and is not faster yet (profiles/r1_f_prefilter_engine.md).
 //
 // The three-term engine (topk_tc16.cu) spends three tensor MACs per fp32-faithful MAC on
 // every (query, key) pair, although only ~k of the ~10^4 pairs of a query matter.  This
@@ -11,19 +13,24 @@
 //   superset: if theta' is the k-th largest a' of a query, every member j of the exact top-k has
 //       a'(j) >= theta' - 2 eps.  (The k keys with a' >= theta' have a >= theta' - eps, so the exact
 //       k-th value is >= theta' - eps, so a(j) >= theta' - eps, so a'(j) >= theta' - 2 eps.)
-//       Every epilogue thread keeps the KP best a' of its share of the keys (sorted, registers);
-//       nothing is merged here -- the 4 partial lists per (query, group) go to the workspace.
+//       Every epilogue thread keeps the KP best a' of its share of the keys (MinList: unsorted slots tagged in
+//       the low mantissa bits, sorted once at the end); nothing is merged here -- the 4 partial lists per
+//       (query, group) go to the workspace.  The 4 threads of a query share lower bounds of theta' through
+//       shared memory (same-position seeds + running (k/4)-th values), so that nothing at or below
+//       bound - 2 eps is inserted; key rows rotate between the warpgroups from entry to entry, or the best rows
+//       of every frame would pile up in one list.
 //   stage B (rescore_kernel, one warp per query): theta' from the partial lists, the superset
 //       {a' >= theta' - 2 eps} (12 candidates on average for k = 10), the exact value
 //       <hi_q + 2^-11 lo_q, hi_j + 2^-11 lo_j> in fp32 for each of them, the exact top-k of those.
 //   stage C (exact_scan_kernel): a partial list that is full AND whose last entry is still inside
-//       the 2 eps band may have dropped a superset member; such queries (none in the synthetic
-//       clips at k = 10) are queued by stage B and re-done here by a plain fp32 scan of their keys.
+//       the 2 eps band may have dropped a superset member; such queries (30 of 404 460 on the bench
+//       clip at k = 10) are queued by stage B and re-done here by a plain fp32 scan of their keys.
 // The result is the exact fp32-faithful top-k -- selection and values -- at a third of the tensor
 // work and half the key bytes (only the hi part of a key box is ever staged).
 //
 // CTA anatomy as in topk_tc16.cu: warp 0 TMA producer, warp 1 MMA issuer (TS-form, hi_q resident in
-// tensor memory), 4 epilogue warpgroups, thread = query.  Key boxes are 16 x BH pixels with BH <= 8
+// tensor memory), warps 2-3 set-up, then 4 epilogue warpgroups (640 threads; setmaxnreg moves registers from
+// warpgroup 0 to the epilogue), thread = query.  Key boxes are 16 x BH pixels with BH <= 8
 // (N <= 128): one MMA per 16 channels, two 128-column accumulators ping-pong.
 // TMEM: [0,128) accumulator 0, [128,256) accumulator 1, [256, 256 + C/2) hi_q.
 #include <stdlib.h>

@@ -58,6 +58,7 @@ SIGNATURES = {
     "fgvc_chain_workspace_bytes": (L64, [I, I, I]),
     "fgvc_mask_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, I, P, I, I, I, I, P, P, P, P, L64, P]),
     "fgvc_point_clip_tail": (I, [P, P, I, I, P, P, I, I, P, I, I, F, I, P, I, I, I, I, I, P, P, P, L64, P]),
+    "fgvc_point_clip_tail_shared": (I, [P, P, I, P, P, P, I, I, P, I, I, F, I, P, I, I, I, I, I, P, P, P, L64, P]),
     "fgvc_c2f_scratch_elems": (L64, [I, I]),
     "fgvc_c2f_propagate": (I, [P, I, I, I, I, I, P, I, I, I, P, P, P, P, I, I, I, I, F, P, I, P, P, P, L64, I, P]),
 }

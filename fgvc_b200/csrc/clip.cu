@@ -43,8 +43,8 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
   // the recurrence lives only in the gather: run the chain first ...
   if (chain_ws != nullptr && job_end - job_begin > 1) {
     // ... as ONE persistent kernel with a grid barrier per frame (gather.cu)
-    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, n_pix,
-                                 temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
+    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, nullptr,
+                                 n_pix, temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
     if (rc) return rc;
     if (maps_nchw) {
       rc = launch_labels_to_nchw_jobs(lab_bank, jobs_dev, job_begin, job_end, Lp, L, n_pix, maps_nchw, st);
@@ -71,22 +71,23 @@ extern "C" int fgvc_mask_clip_tail(const float* topk_val, const int32_t* topk_id
 // propagated frame into maps_nchw[slot][L][H*W], then ONE K3 launch (fused up-sample / soft-argmax)
 // over all (frame, point) maps of the range: coords[slot][L][2].  The out_slots of the range must
 // be consecutive (they are frame indices).
-extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
+static int point_clip_tail_impl(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
                                     const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
                                     int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
                                     float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
                                     int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
-                                    void* chain_ws, int64_t chain_ws_bytes, void* stream) {
+                                    void* chain_ws, int64_t chain_ws_bytes, const int32_t* pair_ref, void* stream) {
   FGVC_CHECK_ARG(jobs_dev && jobs_host && maps_nchw && coords && lab_bank, "fgvc_point_clip_tail: null pointer");
   FGVC_CHECK_ARG(job_end > job_begin, "fgvc_point_clip_tail: empty job range");
   const int n_pix = H * W;
   const int slot0 = jobs_host[job_begin].out_slot;
   for (int j = job_begin; j < job_end; ++j)
     FGVC_CHECK_ARG(jobs_host[j].out_slot == slot0 + (j - job_begin), "fgvc_point_clip_tail: out_slots must be consecutive");
-  if (chain_ws != nullptr && job_end - job_begin > 1) {
+  FGVC_CHECK_ARG(pair_ref == nullptr || chain_ws != nullptr, "fgvc_point_clip_tail_shared: needs the chain workspace");
+  if (chain_ws != nullptr && (job_end - job_begin > 1 || pair_ref != nullptr)) {
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, n_pix,
-                                 temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
+    int rc = launch_gather_chain(topk_val, topk_idx, K, groups, jobs_dev, job_begin, job_end, mem_label_slot, pair_ref,
+                                 n_pix, temperature, flags, lab_bank, Lp, chain_ws, chain_ws_bytes, st);
     if (rc) return rc;
     rc = launch_labels_to_nchw_jobs(lab_bank, jobs_dev, job_begin, job_end, Lp, L, n_pix, maps_nchw, st);
     if (rc) return rc;
@@ -102,4 +103,31 @@ extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_i
   }
   return fgvc_heatmap_coords(maps_nchw + (int64_t)slot0 * L * n_pix, (job_end - job_begin) * L, H, W, out_h, out_w,
                              coord_topk, coords + (int64_t)slot0 * L * 2, stream);
+}
+
+extern "C" int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx, int32_t K, int32_t groups,
+                                    const fgvc_job* jobs_dev, const fgvc_job* jobs_host, int32_t job_begin,
+                                    int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
+                                    float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L, int32_t out_h,
+                                    int32_t out_w, int32_t coord_topk, float* maps_nchw, float* coords,
+                                    void* chain_ws, int64_t chain_ws_bytes, void* stream) {
+  return point_clip_tail_impl(topk_val, topk_idx, K, groups, jobs_dev, jobs_host, job_begin, job_end, mem_label_slot, H, W,
+                              temperature, flags, lab_bank, Lp, L, out_h, out_w, coord_topk, maps_nchw, coords, chain_ws,
+                              chain_ws_bytes, nullptr, stream);
+}
+
+// Same with SHARED top-k lists: the jobs of several with_first groups that have the same query frame look at the
+// same memory frames except their first one, so K1 ran once per (query frame, memory frame) pair
+// (one list per pair) and pair_ref[e] names the list of memory entry e of these jobs (indices into
+// topk_val / topk_idx in units of H*W*K).  Needs the chain workspace.
+extern "C" int fgvc_point_clip_tail_shared(const float* topk_val, const int32_t* topk_idx, int32_t K,
+                                           const int32_t* pair_ref, const fgvc_job* jobs_dev, const fgvc_job* jobs_host,
+                                           int32_t job_begin, int32_t job_end, const int32_t* mem_label_slot, int32_t H,
+                                           int32_t W, float temperature, int32_t flags, float* lab_bank, int32_t Lp,
+                                           int32_t L, int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
+                                           float* coords, void* chain_ws, int64_t chain_ws_bytes, void* stream) {
+  FGVC_CHECK_ARG(pair_ref != nullptr, "fgvc_point_clip_tail_shared: null pair_ref");
+  return point_clip_tail_impl(topk_val, topk_idx, K, 1, jobs_dev, jobs_host, job_begin, job_end, mem_label_slot, H, W,
+                              temperature, flags, lab_bank, Lp, L, out_h, out_w, coord_topk, maps_nchw, coords, chain_ws,
+                              chain_ws_bytes, pair_ref, stream);
 }

@@ -114,19 +114,34 @@ template <int K>
 __global__ void __launch_bounds__(256)
 gather_weights_kernel(const float* __restrict__ tv, const int32_t* __restrict__ ti, int k_in, int groups,
                       const fgvc_job* __restrict__ jobs, int job_begin, const int32_t* __restrict__ mem_label,
-                      int n_pix, float temperature, int flags, float* __restrict__ cw, int32_t* __restrict__ crow) {
+                      const int32_t* __restrict__ pair_ref, int n_pix, float temperature, int flags,
+                      float* __restrict__ cw, int32_t* __restrict__ crow) {
   const int jidx = job_begin + blockIdx.y;
   const int q = blockIdx.x * 256 + threadIdx.x;
   if (q >= n_pix) return;
   const fgvc_job job = jobs[jidx];
   TopK<K> top;
   top.init();
-  for (int g = 0; g < groups; ++g) {
-    const int64_t o = (((int64_t)jidx * groups + g) * n_pix + q) * k_in;
-    for (int i = 0; i < k_in; ++i) {
-      const float v = __ldg(tv + o + i);
-      const int id = __ldg(ti + o + i);
-      if (id >= 0 && v > top.thr()) top.push(v, id);
+  if (pair_ref == nullptr) {
+    for (int g = 0; g < groups; ++g) {
+      const int64_t o = (((int64_t)jidx * groups + g) * n_pix + q) * k_in;
+      for (int i = 0; i < k_in; ++i) {
+        const float v = __ldg(tv + o + i);
+        const int id = __ldg(ti + o + i);
+        if (id >= 0 && v > top.thr()) top.push(v, id);
+      }
+    }
+  } else {
+    // shared per-(query frame, memory frame) lists: entry e of this job reads list pair_ref[e]; the key pixel
+    // is kept, the position becomes the entry's position in THIS job's memory list
+    for (int e = job.mem_begin; e < job.mem_end; ++e) {
+      const int64_t o = ((int64_t)__ldg(pair_ref + e) * n_pix + q) * k_in;
+      for (int i = 0; i < k_in; ++i) {
+        const float v = __ldg(tv + o + i);
+        const int id = __ldg(ti + o + i);
+        if (id < 0 || !(v > top.thr())) break;            // the lists are sorted
+        top.push(v, (e - job.mem_begin) * n_pix + id % n_pix);
+      }
     }
   }
   float a[K];
@@ -229,16 +244,16 @@ int64_t chain_workspace_bytes(int n_jobs, int n_pix, int K) {
 
 template <int K>
 static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int groups, const fgvc_job* jobs, int job_begin,
-                          int n, const int32_t* mem_label, int n_pix, float temperature, int flags, float* lab, int Lp,
-                          void* ws, cudaStream_t st) {
+                          int n, const int32_t* mem_label, const int32_t* pair_ref, int n_pix, float temperature,
+                          int flags, float* lab, int Lp, void* ws, cudaStream_t st) {
   const int64_t cells = (int64_t)n * n_pix * K;
   float* cw = reinterpret_cast<float*>(ws);
   int32_t* crow = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ws) + cells * 4);
   unsigned int* barrier = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + cells * 8);
   FGVC_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
   dim3 gw(cdiv(n_pix, 256), n);
-  gather_weights_kernel<K><<<gw, 256, 0, st>>>(tv, ti, k_in, groups, jobs, job_begin, mem_label, n_pix, temperature,
-                                               flags, cw, crow);
+  gather_weights_kernel<K><<<gw, 256, 0, st>>>(tv, ti, k_in, groups, jobs, job_begin, mem_label, pair_ref, n_pix,
+                                               temperature, flags, cw, crow);
   FGVC_LAUNCH_CHECK();
   // all CTAs must be co-resident (they spin on the grid barrier): cooperative launch, sized from the occupancy
   static int max_ctas = 0;
@@ -264,15 +279,15 @@ static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int grou
 
 // K1b for the consecutive jobs [job_begin, job_end) as one persistent chain (see above)
 int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, const fgvc_job* jobs, int job_begin,
-                        int job_end, const int32_t* mem_label, int n_pix, float temperature, int flags, float* lab,
-                        int Lp, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                        int job_end, const int32_t* mem_label, const int32_t* pair_ref, int n_pix, float temperature,
+                        int flags, float* lab, int Lp, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const int n = job_end - job_begin;
   FGVC_CHECK_ARG(ws != nullptr && ws_bytes >= chain_workspace_bytes(n, n_pix, K),
                  "gather chain: workspace of %lld bytes needed (fgvc_chain_workspace_bytes)",
                  (long long)chain_workspace_bytes(n, n_pix, K));
-  if (K <= 4) return launch_chain_t<4>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
-  if (K <= 10) return launch_chain_t<10>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
-  return launch_chain_t<16>(tv, ti, K, groups, jobs, job_begin, n, mem_label, n_pix, temperature, flags, lab, Lp, ws, st);
+  if (K <= 4) return launch_chain_t<4>(tv, ti, K, groups, jobs, job_begin, n, mem_label, pair_ref, n_pix, temperature, flags, lab, Lp, ws, st);
+  if (K <= 10) return launch_chain_t<10>(tv, ti, K, groups, jobs, job_begin, n, mem_label, pair_ref, n_pix, temperature, flags, lab, Lp, ws, st);
+  return launch_chain_t<16>(tv, ti, K, groups, jobs, job_begin, n, mem_label, pair_ref, n_pix, temperature, flags, lab, Lp, ws, st);
 }
 
 }  // namespace fgvc

@@ -119,6 +119,16 @@ class JobTable:
         self._packed = {}
         return len(self.jobs) - 1
 
+    def add_raw(self, q_slot, raw_feat_entries, out_slot):
+        """A job whose memory entries already carry their FGVC_MEM_UNMASKED flags (label slots = feature slots)."""
+        b = len(self.mem_feat)
+        self.mem_feat.extend(int(r) for r in raw_feat_entries)
+        self.mem_label.extend(int(r) & ~_lib.MEM_UNMASKED for r in raw_feat_entries)
+        self.jobs.append((int(q_slot), b, b + len(raw_feat_entries), int(out_slot)))
+        self._dev = None
+        self._packed = {}
+        return len(self.jobs) - 1
+
     def __len__(self):
         return len(self.jobs)
 
@@ -343,10 +353,37 @@ def pick_packing(table, j0, j1, H, W, radius, mode):
     return best
 
 
-def chain_workspace(dev, n_jobs, n_pix, K, flags=0):
+def shared_pair_table(table, spans, T):
+    """Several ``with_first`` groups of one clip: the jobs (group g, query frame t) of different groups see the same
+    memory frames except their first one, so the label-independent K1 work is shared -- run it once per query frame
+    over the UNION of the groups' memory entries, one list per (query frame, memory entry) pair, and let the tail
+    merge each job's lists.  Returns (utable, Gmax, pair_ref) or None when sharing would not pay:
+      utable   : JobTable with one job per query frame t, entries = sorted unique (frame, mask flag) of all groups;
+      pair_ref : for every memory entry of ``table`` the index (u_job * Gmax + position in the union) of its list."""
+    by_t = {}
+    for j, (q_slot, b, e, _) in enumerate(table.jobs):
+        by_t.setdefault(q_slot, set()).update(table.mem_feat[b:e])
+    if len(table) < 1.8 * len(by_t):
+        return None
+    gmax = max(len(v) for v in by_t.values())
+    if gmax > 64:
+        return None
+    utable, where = JobTable(), {}
+    for u, t in enumerate(sorted(by_t)):
+        ent = sorted(by_t[t], key=lambda r: (r & ~_lib.MEM_UNMASKED, 0 if (r & _lib.MEM_UNMASKED) else 1))
+        utable.add_raw(t, ent, t)
+        for i, r in enumerate(ent):
+            where[(t, r)] = u * gmax + i
+    pair_ref = []
+    for (q_slot, b, e, _) in table.jobs:
+        pair_ref.extend(where[(q_slot, r)] for r in table.mem_feat[b:e])
+    return utable, gmax, pair_ref
+
+
+def chain_workspace(dev, n_jobs, n_pix, K, flags=0, force=False):
     """(pointer, bytes) of the scratch that lets a clip tail run its gather chain as one persistent kernel;
     (None, 0) = per-frame launches (hard propagation decodes between frames, single-frame ranges gain nothing)."""
-    if n_jobs <= 1 or (flags & _lib.HARD_PROP) or os.environ.get("FGVC_NO_CHAIN") == "1":
+    if not force and (n_jobs <= 1 or (flags & _lib.HARD_PROP) or os.environ.get("FGVC_NO_CHAIN") == "1"):
         return None, 0
     nbytes = int(_lib.load().fgvc_chain_workspace_bytes(int(n_jobs), int(n_pix), int(K)))
     ws = _CHAIN_WS.get(_ws_key(dev))
@@ -357,7 +394,7 @@ def chain_workspace(dev, n_jobs, n_pix, K, flags=0):
 
 
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
-                  job_range=None):
+                  job_range=None, pack=True):
     """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch.  ``AUTO``
     = the exact tensor engine of the bank format, else the CUDA-core engine; ``ENGINE_PREFILTER`` (one fp16
     tensor MAC per pair + exact rescoring; F16 banks of unit rows) is explicit."""
@@ -372,7 +409,7 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
     # fp16 tensor engine: pack J consecutive jobs into one query tile when that saves tensor work (topk_tc16g.cu)
-    if engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05) and bank.fmt == _lib.BANK_F16 and \
+    if pack and engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05) and bank.fmt == _lib.BANK_F16 and \
             _lib.load().fgvc_tc_supported(bank.fmt, bank.H, bank.W, bank.C, int(K)):
         J = pick_packing(table, j0, j1, bank.H, bank.W, int(radius), mode)
         if J > 1:

@@ -12,6 +12,8 @@ What changes relative to the reference loop (results identical, see tests):
   * heat-maps are never up-sampled into a [T,P,h,w] tensor nor shipped to the host:
     K3 fuses the bilinear up-sampling with the top-5 soft-argmax (:396-406, :172-191).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -107,11 +109,23 @@ class VanillaTracker(nn.Module):
                 mem = engine.memory_frames(t, precede, with_first_mem, first=t0)
                 table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
         outs = []
+        radius = (nr // 2) if nr is not None else 1
+        shared = None
         if len(table) == 0:
             lists = None
         else:
-            lists = engine.affinity_topk(bank, table, (nr // 2) if nr is not None else 1, cfg.topk,
-                                         cfg.get("mask_mode", "circle"), engine=self.engine_id)
+            # several groups: the label-independent K1 work is shared between the groups (one list per
+            # (query frame, memory frame) pair); FGVC_NO_SHARE=1 keeps one K1 job per (group, frame)
+            if len(groups) > 1 and os.environ.get("FGVC_NO_SHARE") != "1":
+                shared = engine.shared_pair_table(table, spans, T)
+            if shared is not None:
+                utable, gmax, pair_ref = shared
+                lists = engine.affinity_topk(bank, utable, radius, cfg.topk, cfg.get("mask_mode", "circle"), groups=gmax,
+                                             engine=self.engine_id, pack=False)
+                pair_ref = torch.tensor(pair_ref, dtype=torch.int32, device=dev)
+            else:
+                lists = engine.affinity_topk(bank, table, radius, cfg.topk, cfg.get("mask_mode", "circle"),
+                                             engine=self.engine_id)
         jobs_dev, _, mem_label = table.device(dev) if len(table) else (None, None, None)
         jobs_host = torch.tensor(table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
         for (j0, t0), (_, pts) in zip(spans, groups):
@@ -123,11 +137,19 @@ class VanillaTracker(nn.Module):
             coords[t0] = engine.gaussian_coords(pts, (h, w))
             if T - t0 > 1:
                 scratch = torch.empty(T, P, Hf, Wf, dtype=torch.float32, device=dev)   # NCHW maps of every frame
-                _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
-                          _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
-                          temperature, flags, _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
-                          _lib.ptr(coords), *engine.chain_workspace(dev, T - t0 - 1, Hf * Wf, lists.K, flags),
-                          _lib.stream_ptr())
+                if shared is not None:
+                    _lib.call("fgvc_point_clip_tail_shared", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K,
+                              _lib.ptr(pair_ref), _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1),
+                              _lib.ptr(mem_label), Hf, Wf, temperature, flags, _lib.ptr(labels.buf), labels.Lp, P, h, w, 5,
+                              _lib.ptr(scratch), _lib.ptr(coords),
+                              *engine.chain_workspace(dev, T - t0 - 1, Hf * Wf, lists.K, flags, force=True),
+                              _lib.stream_ptr())
+                else:
+                    _lib.call("fgvc_point_clip_tail", _lib.ptr(lists.val), _lib.ptr(lists.idx), lists.K, lists.groups,
+                              _lib.ptr(jobs_dev), _lib.ptr(jobs_host), j0, j0 + (T - t0 - 1), _lib.ptr(mem_label), Hf, Wf,
+                              temperature, flags, _lib.ptr(labels.buf), labels.Lp, P, h, w, 5, _lib.ptr(scratch),
+                              _lib.ptr(coords), *engine.chain_workspace(dev, T - t0 - 1, Hf * Wf, lists.K, flags),
+                              _lib.stream_ptr())
             outs.append(coords.double())
         return outs
 

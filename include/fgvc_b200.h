@@ -251,6 +251,19 @@ FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx
                          int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
                          float* coords, void* chain_ws, int64_t chain_ws_bytes, void* stream);
 
+/* Point tail on SHARED top-k lists.  Jobs of different with_first groups with the same query frame use the same
+ * memory frames except their first one, so K1 is run once per query frame over the union of those frames with one
+ * group per memory entry (fgvc_affinity_topk, groups = longest union): one list per (query frame, memory frame) pair.
+ * pair_ref[e] = index of the list (in units of H*W*K elements of topk_val / topk_idx) for memory entry e of the
+ * per-group job table; the tail merges each job's lists, re-basing the positions to the job's own memory list.
+ * chain_ws is required. */
+FGVC_API int fgvc_point_clip_tail_shared(const float* topk_val, const int32_t* topk_idx, int32_t K,
+                         const int32_t* pair_ref, const fgvc_job* jobs_dev, const fgvc_job* jobs_host,
+                         int32_t job_begin, int32_t job_end, const int32_t* mem_label_slot, int32_t H, int32_t W,
+                         float temperature, int32_t flags, float* lab_bank, int32_t Lp, int32_t L,
+                         int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
+                         float* coords, void* chain_ws, int64_t chain_ws_bytes, void* stream);
+
 /* K2 -- coarse-to-fine propagation (local_attention.py:721-880), single query frame.
  * Coarse stage = per-memory-frame masked argmax on the coarse bank (K1 with K=1 per
  * frame); fine stage = (2*radius_fine+1)^2 window of the fine bank centred at

@@ -479,6 +479,28 @@ def test_tracker_matches_reference_golden(golden_dir, tag):
         assert err.max() <= 0.5, err
 
 
+def test_shared_lists_across_groups_equal_per_group_k1(monkeypatch):
+    """Points queried at different frames form with_first groups (vanilla_tracker.py:249-295).  The shared path
+    (one K1 list per (query frame, memory frame) pair, merged per job by the tail) must track exactly like one K1
+    job per (group, frame)."""
+    import fgvc_b200
+    g = torch.Generator().manual_seed(41)
+    T, C, Hf, Wf, stride = 10, 64, 24, 32, 2
+    feats = _coherent(g, T, C, Hf, Wf).cuda()
+    cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=10, with_first=True, with_first_neighbor=False)
+    trk = fgvc_b200.VanillaTracker(backbone=torch.nn.Identity(), test_cfg=cfg)
+    groups = [(t0, torch.rand(3 + t0, 2, generator=g) * torch.tensor([Wf * stride - 1.0, Hf * stride - 1.0]))
+              for t0 in (0, 1, 4, 5, 7)]
+    monkeypatch.delenv("FGVC_NO_SHARE", raising=False)
+    shared = trk.propagate_points(feats, groups, (Hf * stride, Wf * stride))
+    monkeypatch.setenv("FGVC_NO_SHARE", "1")
+    plain = trk.propagate_points(feats, groups, (Hf * stride, Wf * stride))
+    monkeypatch.delenv("FGVC_NO_SHARE", raising=False)
+    for a, b in zip(shared, plain):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) < 1e-3            # exact ties may enter the lists in another order
+
+
 def test_forward_test_contract_and_oracle():
     import fgvc_b200
     torch.manual_seed(0)

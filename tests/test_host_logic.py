@@ -69,6 +69,32 @@ def test_job_packing_tables_reproduce_every_memory_list():
     # long memories pack, short ones do not (cost model over the exact box counts needs the library: skipped here)
 
 
+def test_shared_pair_table_maps_every_entry_to_its_union_list():
+    """engine.shared_pair_table: several with_first groups share K1 per (query frame, memory frame) pair."""
+    T, precede = 12, 3
+    tb, spans = engine.JobTable(), []
+    for t0 in (0, 2, 5, 6):
+        spans.append((len(tb), t0))
+        for t in range(t0 + 1, T):
+            mem = engine.memory_frames(t, precede, True, first=t0)
+            tb.add(t, mem, mem, t, unmasked=1)
+    ut, g, pr = engine.shared_pair_table(tb, spans, T)
+    assert len(ut) == T - 1 and len(pr) == len(tb.mem_feat) and g == ut.max_mem
+    for (q, b, e, _) in tb.jobs:
+        for k in range(b, e):
+            u, i = divmod(pr[k], g)
+            uq, ub, ue, _ = ut.jobs[u]
+            assert uq == q and ub + i < ue and ut.mem_feat[ub + i] == tb.mem_feat[k]
+    for (_, b, e, _) in ut.jobs:                       # union entries are unique
+        assert len(set(ut.mem_feat[b:e])) == e - b
+    # a single group shares nothing: not worth it
+    one = engine.JobTable()
+    for t in range(1, T):
+        mem = engine.memory_frames(t, precede, True)
+        one.add(t, mem, mem, t)
+    assert engine.shared_pair_table(one, [(0, 0)], T) is None
+
+
 def test_pick_groups_fills_the_chip():
     assert engine.pick_groups(1, 60, 107, 21) >= 2          # one DAVIS frame: split the memory
     assert engine.pick_groups(63, 60, 107, 21) == 1         # a whole clip: 3528 CTAs = 23.8 waves already

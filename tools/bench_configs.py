@@ -19,6 +19,8 @@ from fgvc_b200 import _lib, synthetic as S  # noqa: E402
 
 CFGS = {
     "cfg3": dict(hw=(256, 256), T=50, P=256, nr=30, precede=5),
+    # same clip, query times uniform in [0, T/2) (TAP-Vid query_mode="first": a with_first group per query frame)
+    "cfg3g": dict(hw=(256, 256), T=50, P=256, nr=30, precede=5, spread=True),
     "cfg4": dict(hw=(320, 320), T=32, P=15, nr=30, precede=5),
     "cfg5s": dict(hw=(256, 256), T=250, P=128, nr=30, precede=5),
     # BASELINE config 5 memory-length sweep (same 1/8 point shard)
@@ -37,11 +39,11 @@ def run_points(name, reps=3):
     feats = S.encode(enc, frames, batch=4)
     if feats.shape[0] < c["T"]:                      # long clips: tile the encoded frames
         feats = feats.repeat((c["T"] + feats.shape[0] - 1) // feats.shape[0], 1, 1, 1)[: c["T"]].contiguous()
-    qp = S.query_points(c["P"], c["T"], h, w, seed=1)
+    qp = S.query_points(c["P"], c["T"], h, w, seed=1, first_frame_only=not c.get("spread", False))
     cfg = dict(precede_frames=c["precede"], topk=10, temperature=0.07, neighbor_range=c["nr"], with_first=True,
                with_first_neighbor=True)
     trk = fgvc_b200.VanillaTracker(backbone=torch.nn.Identity(), test_cfg=cfg)
-    groups = [(0, qp[:, 1:].to(dev))]
+    groups = [(int(t0), qp[qp[:, 0] == t0][:, 1:].to(dev)) for t0 in sorted(set(qp[:, 0].tolist()))]
     trk.propagate_points(feats, groups, (h, w))
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
@@ -51,7 +53,8 @@ def run_points(name, reps=3):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
     print(json.dumps(dict(config=name, frames_per_s=(c["T"] - 1) / dt, ms_per_clip=dt * 1e3,
-                          launches_per_clip=(_lib.launch_count() - n0) // reps, feat=list(feats.shape), P=c["P"])))
+                          launches_per_clip=(_lib.launch_count() - n0) // reps, feat=list(feats.shape), P=c["P"],
+                          groups=len(groups))))
 
 
 def run_c2f(reps=5):

@@ -388,7 +388,9 @@ def test_gaussian_labels_and_coords():
     from fgvc_b200 import engine
     pts = torch.tensor([[10.3, 20.6], [50.1, 3.4], [0.2, 0.45], [78.9, 62.7]])   # no exactly equidistant pixels
     h, w, stride = 64, 80, 4
-    full, small = O.gaussian_labels(pts, h, w, stride)
+    # expected maps through the float64 exp (rounded to fp32 at the end): on the GPU boxes the host's vectorised fp32
+    # exp was observed, once in ~7 runs of the suite, 1e-4 off on single elements -- the kernel's value was the right one
+    full, small = O.gaussian_labels(pts.double(), h, w, stride)
     bank = engine.LabelBank(2, 4, h // stride, w // stride, "cuda")
     bank.put_gaussians(pts, 1, stride)
     assert (bank.get_nchw(1).cpu() - small).abs().max() < 1e-6

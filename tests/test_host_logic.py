@@ -69,6 +69,30 @@ def test_job_packing_tables_reproduce_every_memory_list():
     # long memories pack, short ones do not (cost model over the exact box counts needs the library: skipped here)
 
 
+def test_pick_packing_follows_the_memory_length():
+    """engine.pick_packing (cost model over the exact key-box counts; needs the library, no GPU): long memories pack
+    several consecutive query frames per tile, short ones do not; FGVC_PACK forces it."""
+    def table(T, precede):
+        tb = engine.JobTable()
+        for t in range(1, T):
+            mem = engine.memory_frames(t, precede, True)
+            tb.add(t, mem, mem, t)
+        return tb
+    long_mem, short_mem = table(64, 20), table(50, 5)
+    assert engine.pick_packing(long_mem, 0, len(long_mem), 60, 107, 12, 0) in (2, 4)
+    assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0) == 1
+    assert engine.pick_packing(long_mem, 3, 4, 60, 107, 12, 0) == 1            # a single job has nothing to share
+    # exact accounting used by bench.py: packing must reduce the dense pairs of the long-memory clip
+    d1 = engine.dense_pairs(long_mem, 0, len(long_mem), 60, 107, 12, 0, 1)
+    d4 = engine.dense_pairs(long_mem, 0, len(long_mem), 60, 107, 12, 0, 4)
+    assert 0.7 * d1 < d4 < 0.9 * d1
+    os.environ["FGVC_PACK"] = "2"
+    try:
+        assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0) == 2
+    finally:
+        del os.environ["FGVC_PACK"]
+
+
 def test_shared_pair_table_maps_every_entry_to_its_union_list():
     """engine.shared_pair_table: several with_first groups share K1 per (query frame, memory frame) pair."""
     T, precede = 12, 3

@@ -401,9 +401,12 @@ __global__ void __launch_bounds__(256)
 decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int L,
                           int Lp, int H, int W, int out_h, int out_w, const uint32_t* __restrict__ minmax,
                           uint8_t* __restrict__ masks) {
-  extern __shared__ float smm[];       // [2L] decoded min / max
+  extern __shared__ float smm[];       // [2L] decoded min / max, [L] reciprocal of the range
+  float* srcp = smm + 2 * L;
   const uint32_t* mm = minmax + (int64_t)blockIdx.y * 2 * L;
   for (int i = threadIdx.x; i < 2 * L; i += 256) smm[i] = key2f(__ldg(mm + i));
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += 256) srcp[i] = __frcp_rn((smm[L + i] - smm[i]) + 1e-12f);
   __syncthreads();
   const int o = blockIdx.x * 256 + threadIdx.x;
   if (o >= out_h * out_w) return;
@@ -425,7 +428,13 @@ decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restr
       if (l < L) {
         float v = v4[k];
         const float mn = smm[l], mx = smm[L + l];
-        if (mx > 0.f) v = __fdiv_rn(v - mn, (mx - mn) + 1e-12f);
+        if (mx > 0.f) {
+          // The exact (correctly rounded) division is only needed for channels that can still win: the product
+          // with the rounded reciprocal is within 2 ulp of the quotient (which lies in [0, 1]), so a channel whose
+          // product is more than 1e-6 below the best exact quotient so far cannot reach it.  Same arg-max, bit for bit.
+          if ((v - mn) * srcp[l] < best - 1e-6f) continue;
+          v = __fdiv_rn(v - mn, (mx - mn) + 1e-12f);
+        }
         if (v > best) { best = v; arg = l; }
       }
     }
@@ -449,7 +458,7 @@ int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin
   decode_minmax_jobs_kernel<<<grid_cells, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w,
                                                                minmax);
   FGVC_LAUNCH_CHECK();
-  decode_argmax_jobs_kernel<<<grid, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
+  decode_argmax_jobs_kernel<<<grid, 256, 3 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
                                                          masks);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;

@@ -168,7 +168,8 @@ FGVC_API int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, i
                        float* topk_val, int32_t* topk_idx, int32_t engine, int32_t unit_rows,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
-/* K1 on job-packed tiles (F16 bank, tcgen05 fp16 three-term engine only): same output as fgvc_affinity_topk
+/* K1 on job-packed tiles (F16 bank, tcgen05 fp16 three-term engine only; local_attention.py:318-356 for several
+ * consecutive frames of the loop vanilla_tracker.py:345-366 at once): same output as fgvc_affinity_topk
  * for the jobs named by the tile groups (lists are written at [job][group][Nq][K] by job index).  jobs_per_tile in
  * {1, 2, 4}: 128 tile rows = jobs_per_tile jobs x 128 / jobs_per_tile pixels (16x8 | 8x8 | 8x4 block).
  * fgvc_packed_tile_shape reports the pixel block and key-box height the launcher will use (for costing). */
@@ -251,7 +252,8 @@ FGVC_API int fgvc_point_clip_tail(const float* topk_val, const int32_t* topk_idx
                          int32_t out_h, int32_t out_w, int32_t coord_topk, float* maps_nchw,
                          float* coords, void* chain_ws, int64_t chain_ws_bytes, void* stream);
 
-/* Point tail on SHARED top-k lists.  Jobs of different with_first groups with the same query frame use the same
+/* Point tail on SHARED top-k lists (the grouping loop of VanillaTracker.forward_test, vanilla_tracker.py:249-295, which
+ * re-runs forward_test_main per unique query frame).  Jobs of different with_first groups with the same query frame use the same
  * memory frames except their first one, so K1 is run once per query frame over the union of those frames with one
  * group per memory entry (fgvc_affinity_topk, groups = longest union): one list per (query frame, memory frame) pair.
  * pair_ref[e] = index of the list (in units of H*W*K elements of topk_val / topk_idx) for memory entry e of the

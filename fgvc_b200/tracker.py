@@ -128,13 +128,18 @@ class VanillaTracker(nn.Module):
                                              engine=self.engine_id)
         jobs_dev, _, mem_label = table.device(dev) if len(table) else (None, None, None)
         jobs_host = torch.tensor(table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
+        # coordinates of the query frames (soft-argmax of the analytic gaussian, :321-343): one launch for all groups
+        all_pts = torch.cat([pts.to(device=dev, dtype=torch.float32) for _, pts in groups], dim=0) if groups else None
+        all_c0 = engine.gaussian_coords(all_pts, (h, w)) if groups and all_pts.shape[0] else None
+        p_off = 0
         for (j0, t0), (_, pts) in zip(spans, groups):
             P = pts.shape[0]
-            pts = pts.to(device=dev, dtype=torch.float32)
+            pts = all_pts[p_off:p_off + P]
             labels = LabelBank(T, P, Hf, Wf, dev)
             labels.put_gaussians(pts, t0, stride)
             coords = torch.zeros(T, P, 2, dtype=torch.float32, device=dev)
-            coords[t0] = engine.gaussian_coords(pts, (h, w))
+            coords[t0] = all_c0[p_off:p_off + P]
+            p_off += P
             if T - t0 > 1:
                 scratch = torch.empty(T, P, Hf, Wf, dtype=torch.float32, device=dev)   # NCHW maps of every frame
                 if shared is not None:

@@ -102,6 +102,19 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
   const int per = (n_mem + p.groups - 1) / p.groups;
   const int e_lo = job.mem_begin + g * per;
   const int e_hi = min(job.mem_end, e_lo + per);
+  if (e_lo >= e_hi) {
+    // This (job, group) has no memory entry (more groups than entries: per-entry lists of a short memory).  Block
+    // uniform and before any barrier / tensor-memory allocation: write the empty lists and leave.
+    if (threadIdx.x < 128) {
+      const int m = threadIdx.x;
+      const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
+      if (qy < p.H && qx < p.W) {
+        const int64_t o = (((int64_t)blockIdx.z * p.groups + g) * p.n_pix + qy * p.W + qx) * p.k_out;
+        for (int i = 0; i < p.k_out; ++i) { p.tv[o + i] = -INFINITY; p.ti[o + i] = -1; }
+      }
+    }
+    return;
+  }
   const int N = 16 * p.BH;
   const int n_kc = p.C / 64;
   // one stage = one whole key box (all C channels: n_kc chunks of 16 KB), so the single issuing

@@ -199,7 +199,7 @@ def run_ours(args):
     feats, onehot = build_inputs(dev, seed=1000 + rank)
     T = WORK["clip_frames"]
     H, W = WORK["feat_hw"]
-    eng = {"auto": _lib.ENGINE_AUTO, "prefilter": _lib.ENGINE_PREFILTER}[args.engine]
+    eng = _lib.ENGINE_AUTO
     clip = engine.MaskClipPropagator(T, WORK["channels"], H, W, WORK["objects"], WORK["image_hw"], CFG, dev,
                                      engine_id=eng, split=args.split)
     split = clip.bank.split
@@ -286,17 +286,15 @@ def run_ours(args):
         # dense pairs the engine multiplies: job-packed tiles for the fp16 engine (csrc/topk_tc16g.cu)
         mode_id = _lib.MASK_CIRCLE
         r = WORK["neighbor_range"] // 2
-        J = engine.pick_packing(clip.table, 0, len(clip.table), H, W, r, mode_id) if (split == "f16" and args.engine == "auto") else 1
+        J, aligned = (clip.plan.J, clip.plan.aligned) if split == "f16" else (1, False)
         if split == "f16":
-            dense = engine.dense_pairs(clip.table, 0, len(clip.table), H, W, r, mode_id, J)
+            dense = engine.dense_pairs(clip.table, 0, len(clip.table), H, W, r, mode_id, J, aligned)
         else:
             dense = dense_pairs(H, W, r, split) * work["mem_entries"]
         kname = "affinity_topk_tc16_kernel (K1, fp16 three-term split)" if split == "f16" else \
             "affinity_topk_tc_kernel (K1, 3xTF32)"
-        if split == "f16" and args.engine == "auto" and J > 1:
+        if split == "f16" and J > 1:
             kname = f"affinity_topk_tc16g_kernel (K1, fp16 three-term split, {J} jobs packed per query tile)"
-        if args.engine == "prefilter":
-            kname = "affinity_prefilter_tc16_kernel + rescore_kernel + exact_scan_kernel (K1, experimental prefilter engine)"
         out = dict(metric="propagated frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                    warmup=n_warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype=("f16x3" if split == "f16" else "tf32x3") + " split, fp32 accumulate (fp32-faithful)",
@@ -404,9 +402,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--split", default=None, choices=["f16", "tf32"],
                     help="feature-bank split / tensor engine (default: f16 three-term; tf32 = 3xTF32)")
-    ap.add_argument("--engine", default="auto", choices=["auto", "prefilter"],
-                    help="K1 engine: auto = exact tensor engine of the bank; prefilter = experimental fp16 prefilter + "
-                         "exact rescoring (profiles/r1_f_prefilter_engine.md)")
     ap.add_argument("--profile", action="store_true", help="kernels only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,7 +1,7 @@
 """fgvc_b200 -- B200-native label propagation for FGVC (mmpt): hand-written sm_100a
 kernels behind a C ABI, host side mirroring the reference's operator / tracker / test API.
 """
-from ._lib import ENGINE_AUTO, ENGINE_PREFILTER, ENGINE_SIMT, ENGINE_TCGEN05, FgvcError  # noqa: F401
+from ._lib import ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, FgvcError  # noqa: F401
 from .ops import (compute_affinity, masked_attention_efficient, masked_attention_efficient_c2f,  # noqa: F401
                   masked_attention_efficient_v2, propagate, propagate_temporal, spatial_neighbor)
 from .tracker import B200VanillaTracker, VanillaTracker  # noqa: F401

@@ -11,14 +11,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfgvc_b200.so")
 
 MASK_CIRCLE, MASK_SQUARE = 0, 1
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_PREFILTER = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 BANK_TF32, BANK_F16 = 0, 1
 MEM_UNMASKED = 0x40000000
 WEIGHT_COSINE, SIM_L2, HARD_PROP = 1, 2, 4
 
 
+ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
+
+
 class FgvcError(RuntimeError):
-    pass
+    def __init__(self, msg, rc=None):
+        super().__init__(msg)
+        self.rc = rc
 
 
 class Job(ctypes.Structure):
@@ -43,11 +48,8 @@ SIGNATURES = {
     "fgvc_tc_supported": (I, [I, I, I, I, I]),
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
     "fgvc_affinity_topk": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
-    "fgvc_affinity_topk_workspace_bytes": (L64, [I, I, I, I]),
-    "fgvc_prefilter_supported": (I, [I, I, I, I, I, I]),
-    "fgvc_affinity_topk_ws": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, I, P, L64, P]),
-    "fgvc_affinity_topk_packed": (I, [P, I, I, I, I, P, P, I, P, P, I, I, I, I, I, P, P, P]),
-    "fgvc_packed_tile_shape": (I, [I, I, I, I, I, P, P, P]),
+    "fgvc_affinity_topk_packed": (I, [P, I, I, I, I, P, P, I, P, P, I, I, I, I, I, I, P, P, P]),
+    "fgvc_packed_tile_shape": (I, [I, I, I, I, I, P, P, P, P]),
     "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),
     "fgvc_gather_labels": (I, [P, P, I, I, P, I, I, P, I, F, I, P, I, P]),
     "fgvc_dense_propagate": (I, [P, I, I, I, I, P, I, P, P, I, I, F, I, P, I, P]),
@@ -88,7 +90,7 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().fgvc_last_error().decode(errors="replace")
-        raise FgvcError(f"fgvc_b200 error {rc}: {msg}")
+        raise FgvcError(f"fgvc_b200 error {rc}: {msg}", rc)
 
 
 def call(name, *args):

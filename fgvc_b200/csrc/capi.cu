@@ -96,49 +96,14 @@ extern "C" int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, in
                             K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
 }
 
-extern "C" int64_t fgvc_affinity_topk_workspace_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K) {
-  return tc16p_workspace_bytes(n_jobs, groups, n_query, K);
-}
-
-extern "C" int fgvc_prefilter_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K, int32_t groups) {
-  return (bank_format == FGVC_BANK_F16 && tc16p_supported(H, W, C, K, groups)) ? 1 : 0;
-}
-
-extern "C" int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,
-                                     int32_t C, const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
-                                     int32_t radius, int32_t mask_mode, int32_t K, int32_t groups, float* topk_val,
-                                     int32_t* topk_idx, int32_t engine, int32_t unit_rows, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
-  const bool can = bank_format == FGVC_BANK_F16 && unit_rows != 0 && K >= 1 && K <= 16 &&
-                   tc16p_supported(H, W, C, K, groups);
-  if (engine == FGVC_ENGINE_PREFILTER)
-    FGVC_CHECK_ARG(can, "prefilter engine needs an F16 bank of unit rows, C %% 64 == 0, C <= 256, K <= 16, groups <= 8 "
-                        "(format=%d unit_rows=%d C=%d K=%d groups=%d)", bank_format, unit_rows, C, K, groups);
-  // AUTO stays on the exact engines: measured on B200 (profiles/r1_f_prefilter_engine.md) the prefilter's
-  // tensor work is 3x smaller but its epilogue (list insertions for 32 different queries per warp) is the
-  // bound, so it is not faster yet.  It is selected explicitly.
-  const bool use = engine == FGVC_ENGINE_PREFILTER;
-  if (!use)
-    return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
-                              K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
-  FGVC_CHECK_ARG(feat_bank && jobs && mem_feat_slot && topk_val && topk_idx, "fgvc_affinity_topk_ws: null pointer");
-  FGVC_CHECK_ARG(H > 0 && W > 0 && n_jobs > 0 && n_slots > 0, "fgvc_affinity_topk_ws: bad shape");
-  FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk_ws: radius=%d must be >= 1", radius);
-  FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk_ws: bad mask mode");
-  int rc = launch_affinity_topk_tc16p(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
-                                      groups, topk_val, topk_idx, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (rc != FGVC_ERR_UNSUPPORTED || engine != FGVC_ENGINE_AUTO) return rc;
-  return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
-                            K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
-}
-
 extern "C" int fgvc_packed_tile_shape(int32_t H, int32_t W, int32_t radius, int32_t mask_mode, int32_t jobs_per_tile,
-                                      int32_t* tile_h, int32_t* tile_w, int32_t* box_h) {
-  FGVC_CHECK_ARG(tile_h && tile_w && box_h && H > 0 && W > 0 && radius >= 1, "fgvc_packed_tile_shape: bad arguments");
+                                      int32_t* tile_h, int32_t* tile_w, int32_t* box_h, int32_t* ctas_per_tile) {
+  FGVC_CHECK_ARG(tile_h && tile_w && box_h && ctas_per_tile && H > 0 && W > 0 && radius >= 1,
+                 "fgvc_packed_tile_shape: bad arguments");
   FGVC_CHECK_ARG(jobs_per_tile == 1 || jobs_per_tile == 2 || jobs_per_tile == 4, "fgvc_packed_tile_shape: jobs_per_tile");
-  int a, b, c;
-  packed_tile_shape(H, W, mask_reach(radius, mask_mode), jobs_per_tile, &a, &b, &c);
-  *tile_h = a; *tile_w = b; *box_h = c;
+  int a, b, c, d;
+  packed_tile_shape(H, W, mask_reach(radius, mask_mode), jobs_per_tile, &a, &b, &c, &d);
+  *tile_h = a; *tile_w = b; *box_h = c; *ctas_per_tile = d;
   return FGVC_OK;
 }
 
@@ -146,7 +111,8 @@ extern "C" int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots,
                                          const fgvc_job* jobs, const fgvc_tile_group* tile_groups,
                                          int32_t n_tile_groups, const int32_t* union_feat_slot, const int32_t* union_pos,
                                          int32_t jobs_per_tile, int32_t radius, int32_t mask_mode, int32_t K,
-                                         int32_t groups, float* topk_val, int32_t* topk_idx, void* stream) {
+                                         int32_t groups, int32_t split, float* topk_val, int32_t* topk_idx,
+                                         void* stream) {
   FGVC_CHECK_ARG(feat_bank && jobs && tile_groups && union_feat_slot && union_pos && topk_val && topk_idx,
                  "fgvc_affinity_topk_packed: null pointer");
   FGVC_CHECK_ARG(H > 0 && W > 0 && n_tile_groups > 0 && n_slots > 0, "fgvc_affinity_topk_packed: bad shape");
@@ -155,7 +121,7 @@ extern "C" int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots,
   FGVC_CHECK_ARG(radius >= 1, "fgvc_affinity_topk_packed: radius=%d must be >= 1", radius);
   FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_affinity_topk_packed: bad mask mode");
   return launch_affinity_topk_tc16_packed(feat_bank, n_slots, H, W, C, jobs, tile_groups, n_tile_groups, union_feat_slot,
-                                          union_pos, jobs_per_tile, radius, mask_mode, K, groups, topk_val, topk_idx,
+                                          union_pos, jobs_per_tile, radius, mask_mode, K, groups, split, topk_val, topk_idx,
                                           (cudaStream_t)stream);
 }
 

@@ -43,13 +43,12 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // size in elements of one feature-bank slot: [2][n_pix][C]
 __host__ __device__ inline int64_t feat_slot_floats(int n_pix, int C) { return 2ll * n_pix * C; }
 
-// x = hi + lo * 2^-11 for the fp16 split (hi = fp16(x), lo = fp16((x - hi) * 2^11))
-#define FGVC_F16_LO_SCALE 2048.0f
-#define FGVC_F16_LO_INV (1.0f / 2048.0f)
-// |<hi_q, hi_k> - <q, k>| for unit rows: <= 2^-10 from the two fp16 roundings (Cauchy-Schwarz) plus
-// < 6e-5 of fp32 accumulation over C <= 256 products; the prefilter engine (topk_tc16p.cu) uses this
-// bound with margin
-#define FGVC_PREFILTER_EPS 1.25e-3f
+// fp16 split of the F16 bank: X = 16 x, hi = fp16(X), lo = fp16(X - hi); x = (hi + lo) / 16 (exact in fp32).
+// The 2^4 scale keeps `lo` (<= 2^-11 |X|) a normal fp16 number for every element that matters (|x| >= 2^-7 of a
+// unit row), so all three products of the split can share ONE fp32 accumulator (= 256 x affinity).
+#define FGVC_F16_SCALE 16.0f
+#define FGVC_F16_INV (1.0f / 16.0f)
+#define FGVC_F16_ACC_INV (1.0f / 256.0f)
 
 // 4 consecutive channels of pixel `pix` of slot `slot`, reconstructed to fp32, for either bank format
 template <int FMT>
@@ -69,8 +68,8 @@ __device__ __forceinline__ float4 bank_load4(const void* __restrict__ bank, int 
     uint2 a = __ldg(hi + o), b = __ldg(lo + o);
     float2 a0 = __half22float2(*reinterpret_cast<__half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<__half2*>(&a.y));
     float2 b0 = __half22float2(*reinterpret_cast<__half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<__half2*>(&b.y));
-    return make_float4(fmaf(b0.x, FGVC_F16_LO_INV, a0.x), fmaf(b0.y, FGVC_F16_LO_INV, a0.y),
-                       fmaf(b1.x, FGVC_F16_LO_INV, a1.x), fmaf(b1.y, FGVC_F16_LO_INV, a1.y));
+    return make_float4((a0.x + b0.x) * FGVC_F16_INV, (a0.y + b0.y) * FGVC_F16_INV, (a1.x + b1.x) * FGVC_F16_INV,
+                       (a1.y + b1.y) * FGVC_F16_INV);
   }
 }
 
@@ -155,22 +154,17 @@ bool tc16_supported(int H, int W, int C, int K);
 int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
                               float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st);
-bool tc16p_supported(int H, int W, int C, int K, int groups);
-int64_t tc16p_workspace_bytes(int n_jobs, int groups, int n_pix, int K);
-int launch_affinity_topk_tc16p(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
-                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv,
-                               int32_t* ti, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int64_t chain_workspace_bytes(int n_jobs, int n_pix, int K);
 int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, const fgvc_job* jobs, int job_begin,
                         int job_end, const int32_t* mem_label, const int32_t* pair_ref, int n_pix, float temperature,
                         int flags, float* lab, int Lp, void* ws, int64_t ws_bytes, cudaStream_t st);
 int launch_labels_to_nchw_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int Lp, int L,
                                int n_pix, float* maps_nchw, cudaStream_t st);
-void packed_tile_shape(int H, int W, int reach, int jobs_per_tile, int* QH, int* QW, int* BH);
+void packed_tile_shape(int H, int W, int reach, int jobs_per_tile, int* QH, int* QW, int* BH, int* ncta);
 int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs,
                                      const fgvc_tile_group* tgroups, int n_tgroups, const int32_t* uent,
                                      const int32_t* upos, int jobs_per_tile, int radius, int mode, int K, int groups,
-                                     float* tv, int32_t* ti, cudaStream_t st);
+                                     int split, float* tv, int32_t* ti, cudaStream_t st);
 bool c2f_window_supported(int Hf, int Wf, int Cf, int K, int n_mem);
 int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
                            const fgvc_job& job, const int32_t* mem_feat, const int32_t* best, int rf, int K, int chunks,

@@ -77,11 +77,11 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
       } else {
         __half* hi = reinterpret_cast<__half*>(bank_v) + slot_off;
         __half* lo = hi + (int64_t)n_pix * C;
-        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const float X0 = x0 * FGVC_F16_SCALE, X1 = x1 * FGVC_F16_SCALE;        // exact (power of two)
+        const __half h0 = __float2half_rn(X0), h1 = __float2half_rn(X1);
         *reinterpret_cast<__half2*>(hi + (int64_t)p * C + c) = __halves2half2(h0, h1);
         *reinterpret_cast<__half2*>(lo + (int64_t)p * C + c) =
-            __halves2half2(__float2half_rn((x0 - __half2float(h0)) * FGVC_F16_LO_SCALE),
-                           __float2half_rn((x1 - __half2float(h1)) * FGVC_F16_LO_SCALE));
+            __halves2half2(__float2half_rn(X0 - __half2float(h0)), __float2half_rn(X1 - __half2float(h1)));
       }
     }
   }

@@ -1,65 +1,105 @@
-// K1 (tcgen05 engine, fp16 three-term split): fused affinity + radius mask + running top-K.
+// K1 (tcgen05 engine, fp16 three-term split): fused affinity + radius mask + running top-K.  ONE kernel template for
+//   * plain tiles (one job per query tile), job-packed tiles (J consecutive jobs x a small pixel block per tile),
+//   * single-CTA tiles (128 rows, cta_group::1) and CTA-PAIR tiles (256 rows, cta_group::2: the two SMs of a pair
+//     multiply the SAME key box, each staging half of it),
+//   * the window mode of the coarse-to-fine fine stage (K2).
 //
-// Same contract and the same CTA anatomy as topk_tc.cu (TMA producer warp, MMA issuer warp,
-// 4 epilogue warpgroups, thread = query), but the operands are the F16 bank:
-//     x = hi + 2^-11 * lo,   hi = fp16(x),  lo = fp16((x - hi) * 2^11)
-// -- 11 + 11 significant bits per operand, exactly what the 3xTF32 split carries (rows are
-// unit vectors, so fp16's exponent range is enough).  Three products per K step as before:
-//     D1 = hi_q * hi_k,     D2 = hi_q * lo_k + lo_q * hi_k,     affinity = D1 + 2^-11 * D2
-// Why it is faster (profiles/r1_mma_issue_rates.md): an M=128 tcgen05.mma costs N/2 cycles
-// when A comes from tensor memory and N/2 + 43 when A comes from shared memory.  With fp16
-// BOTH query parts fit in TMEM (2 x C/2 columns, packed two channels per 32-bit cell) next
-// to two accumulators, so every MMA is TS-form and runs at the nominal rate; kind::f16 also
-// contracts 16 channels per instruction instead of 8, and a key costs 4 B per channel
-// instead of 8.  Per K step (16 channels) and key box of N keys:
-//     TS(A = hi_q, B = [hi_k ; lo_k] stacked along N, 2N columns) -> D[0,2N)   = [D1 | hi_q*lo_k]
-//     TS(A = lo_q, B = hi_k,                               N columns) -> D[N,2N) += lo_q*hi_k
-// The hi/lo key rows of a box are one TMA box (the "part" dimension of the 5-D map has
-// extent 2), landing stacked in one 128B-swizzled stage.  No query operand lives in shared
-// memory, so the whole 192 KB ring streams key boxes (3 boxes of 64 KB in flight at C = 256).
-// TMEM: [0,128) accumulator 0, [128,256) accumulator 1, [256,384) hi_q, [384,512) lo_q.
+// Operands are the F16 bank:  X = 16 x,  hi = fp16(X),  lo = fp16(X - hi)  -- 11 + 11 significant bits per
+// operand, what the 3xTF32 split carries (rows are unit vectors, the 2^4 scale keeps `lo` a normal fp16 number).
+// Three products per K step (16 channels), all into ONE fp32 accumulator in tensor memory:
+//     D += hi_q * hi_k;   D += hi_q * lo_k;   D += lo_q * hi_k          (D = 256 * affinity, lo*lo < 2^-22 dropped)
+// Both query parts live in tensor memory (2 x C/2 columns, two channels per 32-bit cell), so every MMA is TS-form:
+// an M = 128 (per CTA) tcgen05.mma then costs N/2 cycles, +43 if A came from shared memory
+// (profiles/r1_mma_issue_rates.md).  TMEM: [0,128) accumulator 0, [128,256) accumulator 1, [256,384) hi_q,
+// [384,512) lo_q.
+//
+// Why CTA pairs.  Measured (profiles/r2_a_l2_bound.md): the single-CTA engine moves 64 KB from L2 into shared
+// memory per 1536 tensor cycles and SM -- 7.1 TB/s over the chip, which is the L2 -> SM fabric limit, with the
+// tensor pipe 63 % busy; loading half of every key box made the same launch 21 % faster.  With cta_group::2 a key
+// box serves 256 query rows and each SM of the pair stages only its half of the keys, so the fabric bytes per MAC
+// halve and the tensor pipe becomes the bound.
+//
+// CTA anatomy (576 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane of the
+// pair's leader CTA), warps 2-17 = epilogue: thread = query row (TMEM lane), warpgroup w owns key rows w, w+4 of a
+// box.  A key box is a spatial rectangle (16 x BH pixels of one memory frame): halos are box coordinates and
+// out-of-image pixels are zero-filled by the TMA unit.  The boxes a tile needs are listed once per CTA (centre-out)
+// and walked by all three roles.  The circle / square mask is one 16-bit interval per (thread, key row); candidates
+// above the thread's running K-th value are inserted into a sorted register list in warp-wide rounds.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
 
 namespace fgvc {
+namespace tc16 {
 
-constexpr int T16_STAGE_BYTES = 16 * 1024;     // 2 parts x 64 keys x 128 B (64 channels of fp16)
-constexpr int T16_STAGES = 12;
-constexpr int T16_MAX_BH = 4;                  // N <= 64, 2N <= 128 accumulator columns
-constexpr int T16_AHI_COL = 256, T16_ALO_COL = 384;
-constexpr int T16_EPI_WG = 4;
-constexpr int T16_THREADS = 64 + 128 * T16_EPI_WG;
-constexpr int T16_MAX_BOXES = 4096;             // per box list (masked halo / whole frame)
-constexpr int T16_AUX_BYTES = 1024 + 2 * T16_MAX_BOXES * 4;
-constexpr int T16_SMEM_BYTES = T16_STAGES * T16_STAGE_BYTES + T16_AUX_BYTES;
+constexpr int RING_BYTES = 192 * 1024;
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_NC = 64;                     // keys of a box staged per CTA (x NCTA = N of the MMA)
+constexpr int AHI_COL = 256, ALO_COL = 384;
+constexpr int EPI_WG = 4;
+constexpr int THREADS = 64 + 128 * EPI_WG;
+constexpr int MAX_BOXES = 4096;                // per box list (masked halo / whole frame)
+constexpr int AUX_BYTES = 1024 + 2 * MAX_BOXES * 4;
+constexpr int SMEM_BYTES = RING_BYTES + AUX_BYTES;
+constexpr int TW_MAX_MEM = 64;                 // window mode: memory entries per call
 
-struct Tc16Params {
-  int H, W, C, n_pix;
+struct Params {
+  int H, W, C, n_pix;          // key grid (window mode: the FINE grid)
   int radius, mode, reach;
-  int QH, QW, qw_shift;
-  int BH;
-  int groups, k_out;
+  int QH, QW, qw_shift;        // pixel block of ONE job inside a tile
+  int lpj_shift;               // log2(tile rows per job): rows = J jobs x (128 * NCTA / J) pixels
+  int BH;                      // key-box height: a box = 16 x BH pixels = N keys, BH / NCTA rows staged per CTA
   int tiles_x;
+  int lists_per_job, split, k_out;   // output lists per job; a tile group's memory list is split `split` ways (grid.y)
   const fgvc_job* jobs;
-  const int32_t* mem_feat;
+  const fgvc_tile_group* tgroups;   // packed tiles (one per grid.z) or nullptr: one job per grid.z
+  const int32_t* ent;               // memory entries: union table (packed) / mem_feat table
+  const int32_t* upos;              // packed: [entry][4] position in job i's own list, -1 = not in it
+  // window mode (K2 fine stage)
+  int HQ, WQ, scale, rf, chunks;
+  fgvc_job job;
+  const int32_t* best;              // [n_mem][HQ * WQ] coarse arg-max key pixel per memory entry
   float* tv;
   int32_t* ti;
   float* dbg;
   int32_t* dbg_meta;
   int dbg_max_boxes;
-  int exp_flags;             // experiments (FGVC_TC16_EXP env): 1 = skip the candidate scan, 2 = skip TMEM loads too
+  int exp_flags;             // experiments (FGVC_TC16_EXP env): 1 = no candidate scan, 2 = no TMEM loads, 4 = half the TMA bytes
 };
 
+// ------------------------------------------------------------------------- PTX wrappers (cta_group aware)
+template <int NCTA>
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (NCTA == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of this thread -> one arrival on `bar` (in both CTAs of a pair)
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_all(uint64_t* bar) {
+  if (NCTA == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c,
                                            const uint4& d) {
@@ -73,124 +113,229 @@ __device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint4& a, const
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `p` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one 64-channel chunk of this CTA's part of a key box -> shared memory; completion bytes go to the LEADER's barrier
+template <int NCTA>
+__device__ __forceinline__ void tma_box(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1, int c2,
+                                        int c3, int c4) {
+  if (NCTA == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 
-template <int K>
-__global__ void __launch_bounds__(T16_THREADS, 1)
-affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __half* __restrict__ bank,
-                          const Tc16Params p) {
+template <int K, int NCTA, bool WIN>
+__global__ void __launch_bounds__(THREADS, 1)
+affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __half* __restrict__ bank, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + T16_STAGES * T16_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + T16_STAGES;
-  uint64_t* tfull_bar = empty_bar + T16_STAGES;   // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + RING_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint64_t* a_bar = tempty_bar + 2;               // query operand written to TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
   int* nbox = reinterpret_cast<int*>(tmem_slot + 2);      // [2] number of boxes in each list
-  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);     // [reach+1] <= 128 entries
+  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);     // [reach+1] <= 128 entries (window mode: rect[4])
   // box lists (by | bx << 16): [0] = radius halo of this query tile minus boxes no query can see,
   // [1] = every box of the frame (unmasked memory entries).  Identical for all memory entries, so
   // the three warp roles just walk a list instead of re-deriving the geometry per box.
-  uint32_t* boxes = reinterpret_cast<uint32_t*>(ring + T16_STAGES * T16_STAGE_BYTES + 1024);
+  // Window mode: ONE list (this CTA's chunk of its entry's rectangle) over both areas.
+  uint32_t* boxes = reinterpret_cast<uint32_t*>(ring + RING_BYTES + 1024);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qy0 = (blockIdx.x / p.tiles_x) * p.QH, qx0 = (blockIdx.x % p.tiles_x) * p.QW;
-  const int g = blockIdx.y;
-  const fgvc_job job = p.jobs[blockIdx.z];
-  const int n_mem = job.mem_end - job.mem_begin;
-  const int per = (n_mem + p.groups - 1) / p.groups;
-  const int e_lo = job.mem_begin + g * per;
-  const int e_hi = min(job.mem_end, e_lo + per);
-  if (e_lo >= e_hi) {
-    // This (job, group) has no memory entry (more groups than entries: per-entry lists of a short memory).  Block
-    // uniform and before any barrier / tensor-memory allocation: write the empty lists and leave.
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int tile = blockIdx.x / NCTA;
+  const int qy0 = (tile / p.tiles_x) * p.QH, qx0 = (tile % p.tiles_x) * p.QW;
+
+  // ---- this CTA's jobs and memory entries
+  fgvc_tile_group tg;
+  int e_lo, e_hi, og = 0;
+  if (WIN) {
+    tg.job[0] = 0; tg.n_jobs = 1;
+    e_lo = p.job.mem_begin + blockIdx.y; e_hi = e_lo + 1;
+  } else {
+    if (p.tgroups) {
+      // heaviest groups first: in clip order the late jobs have the longest memory lists, and a launch that ends
+      // with its longest CTAs pays for them in the tail
+      tg = p.tgroups[gridDim.z - 1 - blockIdx.z];
+    } else {
+      const fgvc_job job = p.jobs[blockIdx.z];
+      tg.job[0] = blockIdx.z; tg.job[1] = tg.job[2] = tg.job[3] = -1;
+      tg.n_jobs = 1; tg.u_begin = job.mem_begin; tg.u_end = job.mem_end; tg.out_group = 0;
+    }
+    const int n_mem = tg.u_end - tg.u_begin;
+    const int per = (n_mem + p.split - 1) / p.split;
+    e_lo = tg.u_begin + blockIdx.y * per;
+    e_hi = min(tg.u_end, e_lo + per);
+    og = tg.out_group * p.split + blockIdx.y;
+  }
+  const int nq_c = WIN ? p.HQ * p.WQ : 0;
+  const int qH = WIN ? p.HQ : p.H, qW = WIN ? p.WQ : p.W;       // query grid
+
+  if (!WIN && e_lo >= e_hi) {
+    // This (tile group, part) has no memory entry (more parts than entries).  Uniform over the CTA pair and before
+    // any barrier / tensor-memory allocation: write the empty lists and leave.
     if (threadIdx.x < 128) {
-      const int m = threadIdx.x;
-      const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
-      if (qy < p.H && qx < p.W) {
-        const int64_t o = (((int64_t)blockIdx.z * p.groups + g) * p.n_pix + qy * p.W + qx) * p.k_out;
+      const int R = (int)rank * 128 + (int)threadIdx.x;
+      const int jm = R >> p.lpj_shift, rm = R & ((1 << p.lpj_shift) - 1);
+      const int jb = jm < tg.n_jobs ? tg.job[jm] : -1;
+      const int qy = qy0 + (rm >> p.qw_shift), qx = qx0 + (rm & (p.QW - 1));
+      if (jb >= 0 && qy < p.H && qx < p.W) {
+        const int64_t o = (((int64_t)jb * p.lists_per_job + og) * p.n_pix + qy * p.W + qx) * p.k_out;
         for (int i = 0; i < p.k_out; ++i) { p.tv[o + i] = -INFINITY; p.ti[o + i] = -1; }
       }
     }
     return;
   }
-  const int N = 16 * p.BH;
+
+  const int NC = 16 * p.BH / NCTA;             // keys of a box staged by this CTA
+  const int N = 16 * p.BH;                     // keys of a box = accumulator columns
   const int n_kc = p.C / 64;
-  // one stage = one whole key box (all C channels: n_kc chunks of 16 KB), so the single issuing
-  // threads pay one barrier round trip per box instead of one per 64 channels
-  const int stage_bytes = n_kc * T16_STAGE_BYTES;
-  const int n_stages = (T16_STAGES * T16_STAGE_BYTES) / stage_bytes;
-  const uint32_t stage_tx = (uint32_t)(2 * N * 128 * n_kc);
+  // one stage = this CTA's part of one whole key box (all C channels: n_kc chunks of [hi rows ; lo rows] x 128 B),
+  // so the single issuing threads pay one barrier round trip per box instead of one per 64 channels
+  const int chunk_bytes = 2 * NC * 128;
+  const int stage_bytes = n_kc * chunk_bytes;
+  const int n_stages = min(MAX_STAGES, RING_BYTES / stage_bytes);
+  const uint32_t stage_tx = (uint32_t)(NCTA * stage_bytes);      // bytes that complete on the leader's barrier
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     for (int s = 0; s < n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * T16_EPI_WG); }
-    mbar_init(a_bar, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * EPI_WG * NCTA); }
+    mbar_init(a_bar, 4 * EPI_WG * NCTA);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  for (int d = threadIdx.x; d <= p.reach; d += T16_THREADS) {
-    int hw = -1;
-    if (p.mode == FGVC_MASK_CIRCLE) {
-      while (hw + 1 <= p.reach && (hw + 1) * (hw + 1) + d * d < p.radius * p.radius) ++hw;
+    if (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     } else {
-      hw = p.radius;
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    halfw[d] = hw;
   }
-  if (warp == 2 || warp == 3) {          // one warp per list
-    const int li = warp - 2;
-    const Walk w = make_walk(p, li ? FGVC_MEM_UNMASKED : 0, qy0, qx0);
-    const int ncols = (w.x_hi - w.x_lo) / 16 + 1, nrows = (w.y_hi - w.y_lo) / p.BH + 1;
-    uint32_t* list = boxes + li * T16_MAX_BOXES;
-    int cnt = 0;
-    for (int base = 0; base < nrows * ncols; base += 32) {
-      const int i = base + lane;
-      const int by = w.y_lo + (i / ncols) * p.BH, bx = w.x_lo + (i % ncols) * 16;
-      const bool keep = i < nrows * ncols && !box_skipped(p, w, by, bx, qy0, qx0);
-      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-      if (keep && pos < T16_MAX_BOXES) list[pos] = (uint32_t)by | ((uint32_t)bx << 16);
-      cnt += __popc(bal);
-    }
-    cnt = min(cnt, T16_MAX_BOXES);
-    __syncwarp();
-    // Centre-out order for the halo list: the best matches of a query sit near its own position, so
-    // walking the boxes nearest to the tile first raises the running K-th values early and the
-    // (divergent, ~80-instruction) list insertions become rare.  Rank sort, n is a few dozen.
-    if (li == 0 && cnt > 1 && cnt <= 128) {
-      const int cy2 = 2 * qy0 + p.QH, cx2 = 2 * qx0 + p.QW;          // twice the tile centre
-      uint32_t mine[4]; int rank[4];
-      for (int t = 0; t < 4; ++t) {
-        const int i = lane + 32 * t;
-        mine[t] = i < cnt ? list[i] : 0u;
-        rank[t] = 0;
+  if constexpr (!WIN) {
+    for (int d = threadIdx.x; d <= p.reach; d += THREADS) {
+      int hw = -1;
+      if (p.mode == FGVC_MASK_CIRCLE) {
+        while (hw + 1 <= p.reach && (hw + 1) * (hw + 1) + d * d < p.radius * p.radius) ++hw;
+      } else {
+        hw = p.radius;
       }
-      for (int j = 0; j < cnt; ++j) {
-        const uint32_t o = list[j];
-        const int oy = 2 * (int)(o & 0xffffu) + p.BH - cy2, ox = 2 * (int)(o >> 16) + 16 - cx2;
-        const int od = oy * oy + ox * ox;
+      halfw[d] = hw;
+    }
+    if (warp == 2 || warp == 3) {          // one warp per list
+      const int li = warp - 2;
+      const Walk w = make_walk(p, li ? FGVC_MEM_UNMASKED : 0, qy0, qx0);
+      const int ncols = (w.x_hi - w.x_lo) / 16 + 1, nrows = (w.y_hi - w.y_lo) / p.BH + 1;
+      uint32_t* list = boxes + li * MAX_BOXES;
+      int cnt = 0;
+      for (int base = 0; base < nrows * ncols; base += 32) {
+        const int i = base + lane;
+        const int by = w.y_lo + (i / ncols) * p.BH, bx = w.x_lo + (i % ncols) * 16;
+        const bool keep = i < nrows * ncols && !box_skipped(p, w, by, bx, qy0, qx0);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (keep && pos < MAX_BOXES) list[pos] = (uint32_t)by | ((uint32_t)bx << 16);
+        cnt += __popc(bal);
+      }
+      cnt = min(cnt, MAX_BOXES);
+      __syncwarp();
+      // Centre-out order for the halo list: the best matches of a query sit near its own position, so
+      // walking the boxes nearest to the tile first raises the running K-th values early and the
+      // (divergent, ~80-instruction) list insertions become rare.  Rank sort, n is a few dozen.
+      if (li == 0 && cnt > 1 && cnt <= 128) {
+        const int cy2 = 2 * qy0 + p.QH, cx2 = 2 * qx0 + p.QW;          // twice the tile centre
+        uint32_t mine[4]; int rnk[4];
         for (int t = 0; t < 4; ++t) {
           const int i = lane + 32 * t;
-          const int my = 2 * (int)(mine[t] & 0xffffu) + p.BH - cy2, mx = 2 * (int)(mine[t] >> 16) + 16 - cx2;
-          const int md = my * my + mx * mx;
-          rank[t] += (od < md || (od == md && j < i)) ? 1 : 0;
+          mine[t] = i < cnt ? list[i] : 0u;
+          rnk[t] = 0;
         }
+        for (int j = 0; j < cnt; ++j) {
+          const uint32_t o = list[j];
+          const int oy = 2 * (int)(o & 0xffffu) + p.BH - cy2, ox = 2 * (int)(o >> 16) + 16 - cx2;
+          const int od = oy * oy + ox * ox;
+          for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            const int my = 2 * (int)(mine[t] & 0xffffu) + p.BH - cy2, mx = 2 * (int)(mine[t] >> 16) + 16 - cx2;
+            const int md = my * my + mx * mx;
+            rnk[t] += (od < md || (od == md && j < i)) ? 1 : 0;
+          }
+        }
+        __syncwarp();
+        for (int t = 0; t < 4; ++t)
+          if (lane + 32 * t < cnt) list[rnk[t]] = mine[t];
       }
-      __syncwarp();
-      for (int t = 0; t < 4; ++t)
-        if (lane + 32 * t < cnt) list[rank[t]] = mine[t];
+      if (lane == 0) nbox[li] = cnt;
     }
-    if (lane == 0) nbox[li] = cnt;
+  } else if (warp >= 2 && warp < 6) {
+    // ---- window mode: bounding rectangle of the tile's window centres in this CTA's memory entry (lane = query)
+    int* rect = halfw;
+    const int m = (warp - 2) * 32 + lane;
+    const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
+    const bool qvalid = qy < p.HQ && qx < p.WQ;
+    int cy_lo = 1 << 30, cy_hi = -1, cx_lo = 1 << 30, cx_hi = -1;
+    if (qvalid) {
+      const int b = max(__ldg(p.best + (int64_t)blockIdx.y * nq_c + qy * p.WQ + qx), 0) % nq_c;
+      cy_lo = cy_hi = (b / p.WQ) * p.scale;
+      cx_lo = cx_hi = (b % p.WQ) * p.scale;
+    }
+    cy_lo = __reduce_min_sync(0xffffffffu, cy_lo); cy_hi = __reduce_max_sync(0xffffffffu, cy_hi);
+    cx_lo = __reduce_min_sync(0xffffffffu, cx_lo); cx_hi = __reduce_max_sync(0xffffffffu, cx_hi);
+    if (warp == 2 && lane < 4) rect[lane] = lane == 0 ? cy_lo : (lane == 1 ? cy_hi : (lane == 2 ? cx_lo : cx_hi));
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (warp != 2 && lane == 0) {
+      atomicMin(rect + 0, cy_lo); atomicMax(rect + 1, cy_hi);
+      atomicMin(rect + 2, cx_lo); atomicMax(rect + 3, cx_hi);
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    // box list: this CTA's chunk of the boxes of the rectangle grown by rf, clipped to the map (warp 2)
+    if (warp == 2) {
+      int cnt = 0;
+      if (rect[1] >= 0) {                                       // (else: no valid query in the tile)
+        const int y_lo = max(0, rect[0] - p.rf), y_hi = min(p.H - 1, rect[1] + p.rf);
+        const int x_lo = max(0, rect[2] - p.rf), x_hi = min(p.W - 1, rect[3] + p.rf);
+        const int ncols = (x_hi - x_lo) / 16 + 1, nrows = (y_hi - y_lo) / p.BH + 1;
+        const int total = nrows * ncols;
+        const int i_lo = (int)((int64_t)total * blockIdx.z / p.chunks), i_hi = (int)((int64_t)total * (blockIdx.z + 1) / p.chunks);
+        for (int i = i_lo + lane; i < i_hi; i += 32) {
+          const int by = y_lo + (i / ncols) * p.BH, bx = x_lo + (i % ncols) * 16;
+          if (i - i_lo < 2 * MAX_BOXES) boxes[i - i_lo] = (uint32_t)by | ((uint32_t)bx << 16);
+        }
+        cnt = min(i_hi - i_lo, 2 * MAX_BOXES);
+      }
+      if (lane == 0) { nbox[0] = cnt; nbox[1] = 0; }
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -200,78 +345,84 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int n_ld = (p.exp_flags & 4) ? max(1, n_kc / 2) : n_kc;     // experiment: half the L2 -> SM bytes
+      const int row_off = (int)rank * (p.BH / NCTA);                     // this CTA's key rows of a box
       for (int e = e_hi - 1; e >= e_lo; --e) {       // newest memory frame first: thresholds rise early
-        const int raw = p.mem_feat[e];
+        const int raw = p.ent[e];
         const int slot = raw & ~FGVC_MEM_UNMASKED;
-        const int li = (raw & FGVC_MEM_UNMASKED) ? 1 : 0;
+        const int li = (!WIN && (raw & FGVC_MEM_UNMASKED)) ? 1 : 0;
         const int nb = nbox[li];
         for (int b = 0; b < nb; ++b) {
-          const uint32_t bb = boxes[li * T16_MAX_BOXES + b];
+          const uint32_t bb = boxes[li * MAX_BOXES + b];
           const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, stage_tx);
-          // per 64-channel chunk one TMA box = (64 channels, 16 x BH pixels, both parts): hi rows then lo rows
-          for (int kc = 0; kc < n_kc; ++kc)
-            tma_load_5d(&tmap_k, full_bar + stage, ring + stage * stage_bytes + kc * T16_STAGE_BYTES, kc * 64, bx, by,
-                        0, slot);
+          const uint32_t fb = NCTA == 2 ? map_to_rank(smem_u32(full_bar + stage), 0) : smem_u32(full_bar + stage);
+          if (rank == 0) mbar_expect_tx(full_bar + stage, stage_tx / n_kc * n_ld);
+          // per 64-channel chunk one TMA box = (64 channels, 16 x BH/NCTA pixels, both parts): hi rows then lo rows
+          for (int kc = 0; kc < n_ld; ++kc)
+            tma_box<NCTA>(&tmap_k, fb, ring + stage * stage_bytes + kc * chunk_bytes, kc * 64, bx, by + row_off, 0, slot);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================================= MMA issuer =====================================
-    if (e_lo < e_hi) {
+    // ================================= MMA issuer (leader CTA of the pair) =====================================
+    if (rank == 0) {
       mbar_wait(a_bar, 0);
       tc_fence_after();
-    }
-    int n_total = 0;                                 // boxes this CTA processes
-    for (int e = e_lo; e < e_hi; ++e) n_total += nbox[(p.mem_feat[e] & FGVC_MEM_UNMASKED) ? 1 : 0];
-    if (elect_one()) {
-      const uint32_t idesc2 = make_idesc_f16(128, 2 * N), idesc1 = make_idesc_f16(128, N);
-      int stage = 0, buf = 0;
-      uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
-      const uint32_t ring_u32 = smem_u32(ring);
-      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-      // The barrier probes of box it+1 are issued while the last MMAs of box it are still queued in
-      // the tensor pipe, so the pipe does not drain during the ~100-cycle try_wait round trips.
-      if (n_total > 0) {
-        mbar_wait(tempty_bar + 0, tphase0 ^ 1);
-        mbar_wait(full_bar + 0, phase);
-        tc_fence_after();
-      }
-      for (int it = 0; it < n_total; ++it) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-        const uint32_t sa = ring_u32 + (uint32_t)(stage * stage_bytes);
-        for (int kc = 0; kc < n_kc; ++kc) {
-          const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * T16_STAGE_BYTES)) >> 4);
-          const uint32_t a_hi = tmem_base + T16_AHI_COL + kc * 32, a_lo = tmem_base + T16_ALO_COL + kc * 32;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
-            if (ks == 3 && kc == n_kc - 1) break;  // the last K step is issued after the probes below
-            const uint64_t o = (uint64_t)(ks * 2);
-            umma_f16_ts(d_tmem, a_hi + ks * 8, b + o, idesc2, (kc | ks) != 0);   // [hi*hi | hi*lo]
-            umma_f16_ts(d_tmem + N, a_lo + ks * 8, b + o, idesc1, 1);            // += lo*hi
-          }
-        }
-        const int nstage = (stage + 1 == n_stages) ? 0 : stage + 1;
-        const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
-        const int nbuf = buf ^ 1;
-        if (it + 1 < n_total) {
-          mbar_wait(tempty_bar + nbuf, (nbuf ? tphase1 : tphase0) ^ 1);   // epilogue drained the other accumulator
-          mbar_wait(full_bar + nstage, nphase);                           // next key box landed
+      int n_total = 0;                                 // boxes this CTA processes
+      for (int e = e_lo; e < e_hi; ++e) n_total += nbox[(!WIN && (p.ent[e] & FGVC_MEM_UNMASKED)) ? 1 : 0];
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_f16(128 * NCTA, N);
+        int stage = 0, buf = 0;
+        uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
+        const uint32_t ring_u32 = smem_u32(ring);
+        const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+        const uint64_t lo_off = (uint64_t)((NC * 128) >> 4);           // lo rows follow the hi rows of a chunk
+        // The barrier probes of box it+1 are issued while the last MMAs of box it are still queued in
+        // the tensor pipe, so the pipe does not drain during the ~100-cycle try_wait round trips.
+        if (n_total > 0) {
+          mbar_wait(tempty_bar + 0, tphase0 ^ 1);
+          mbar_wait(full_bar + 0, phase);
           tc_fence_after();
         }
-        {
-          const int kc = n_kc - 1;
-          const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * T16_STAGE_BYTES)) >> 4);
-          umma_f16_ts(d_tmem, tmem_base + T16_AHI_COL + kc * 32 + 24, b + 6, idesc2, 1);
-          umma_f16_ts(d_tmem + N, tmem_base + T16_ALO_COL + kc * 32 + 24, b + 6, idesc1, 1);
+        for (int it = 0; it < n_total; ++it) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+          const uint32_t sa = ring_u32 + (uint32_t)(stage * stage_bytes);
+          for (int kc = 0; kc < n_kc; ++kc) {
+            const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * chunk_bytes)) >> 4);
+            const uint32_t a_hi = tmem_base + AHI_COL + kc * 32, a_lo = tmem_base + ALO_COL + kc * 32;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
+              if (ks == 3 && kc == n_kc - 1) break;  // the last K step is issued after the probes below
+              const uint64_t o = (uint64_t)(ks * 2);
+              umma_f16_ts<NCTA>(d_tmem, a_hi + ks * 8, b + o, idesc, (kc | ks) != 0);     // hi*hi
+              umma_f16_ts<NCTA>(d_tmem, a_hi + ks * 8, b + lo_off + o, idesc, 1);         // hi*lo
+              umma_f16_ts<NCTA>(d_tmem, a_lo + ks * 8, b + o, idesc, 1);                  // lo*hi
+            }
+          }
+          const int nstage = (stage + 1 == n_stages) ? 0 : stage + 1;
+          const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
+          const int nbuf = buf ^ 1;
+          if (it + 1 < n_total) {
+            mbar_wait(tempty_bar + nbuf, (nbuf ? tphase1 : tphase0) ^ 1);   // epilogue drained the other accumulator
+            mbar_wait(full_bar + nstage, nphase);                           // next key box landed
+            tc_fence_after();
+          }
+          {
+            const int kc = n_kc - 1;
+            const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * chunk_bytes)) >> 4);
+            const uint32_t a_hi = tmem_base + AHI_COL + kc * 32 + 24, a_lo = tmem_base + ALO_COL + kc * 32 + 24;
+            umma_f16_ts<NCTA>(d_tmem, a_hi, b + 6, idesc, 1);
+            umma_f16_ts<NCTA>(d_tmem, a_hi, b + lo_off + 6, idesc, 1);
+            umma_f16_ts<NCTA>(d_tmem, a_lo, b + 6, idesc, 1);
+          }
+          umma_commit_all<NCTA>(empty_bar + stage);     // smem stage free (in both CTAs) once these MMAs retire
+          umma_commit_all<NCTA>(tfull_bar + buf);       // accumulator complete
+          if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+          buf = nbuf; stage = nstage; phase = nphase;
         }
-        umma_commit(empty_bar + stage);     // smem stage free once these MMAs retire
-        umma_commit(tfull_bar + buf);       // accumulator complete
-        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf = nbuf; stage = nstage; phase = nphase;
       }
     }
     __syncwarp();
@@ -280,100 +431,138 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     const int wg = (warp - 2) >> 2;
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
-    const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
-    const bool qvalid = qy < p.H && qx < p.W;
-    if (wg == 0 && e_lo < e_hi) {
-      // both query parts -> tensor memory, two fp16 channels per 32-bit cell (lower channel in the low half)
+    const int R = (int)rank * 128 + m;                      // row of the (pair's) tile
+    const int jm = R >> p.lpj_shift;                        // which job of the group this lane (this whole warp) serves
+    const int rm = R & ((1 << p.lpj_shift) - 1);            // pixel of the block
+    const int jb = WIN ? 0 : (jm < tg.n_jobs ? tg.job[jm] : -1);
+    const int qy = qy0 + (rm >> p.qw_shift), qx = qx0 + (rm & (p.QW - 1));
+    const bool qvalid = jb >= 0 && qy < qH && qx < qW;
+    const uint32_t tempty_l0 = NCTA == 2 ? map_to_rank(smem_u32(tempty_bar + 0), 0) : 0u;   // the leader's barriers
+    const uint32_t tempty_l1 = NCTA == 2 ? map_to_rank(smem_u32(tempty_bar + 1), 0) : 0u;
+    {
+      // both query parts -> tensor memory, two fp16 channels per 32-bit cell (lower channel in the low half).  The four
+      // warps that share a TMEM lane quarter split the channels: 16 cells (64 B of the row) per tcgen05.st.
+      // Window mode: the row is the FINE query feature at (scale * qy, scale * qx)   (local_attention.py:785)
+      const int q_slot = WIN ? p.job.q_slot : (jb >= 0 ? p.jobs[jb].q_slot : 0);
+      const int qpix = !qvalid ? 0 : (WIN ? (qy * p.scale) * p.W + qx * p.scale : qy * p.W + qx);
       const int64_t part = (int64_t)p.n_pix * p.C;
-      const __half* row = bank + (int64_t)job.q_slot * 2 * part + (int64_t)(qvalid ? qy * p.W + qx : 0) * p.C;
+      const __half* row = bank + (int64_t)q_slot * 2 * part + (int64_t)qpix * p.C;
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-      for (int prt = 0; prt < 2; ++prt) {
-        const uint4* src = reinterpret_cast<const uint4*>(row + prt * part);
-        const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (prt ? T16_ALO_COL : T16_AHI_COL);
-        for (int c = 0; c < p.C / 2; c += 16) {          // 16 cells = 32 channels = 4 x uint4
-          uint4 a = z, b = z, c4 = z, d = z;
-          if (qvalid) { a = __ldg(src + c / 4); b = __ldg(src + c / 4 + 1); c4 = __ldg(src + c / 4 + 2); d = __ldg(src + c / 4 + 3); }
-          tmem_st16u(ta + c, a, b, c4, d);
-        }
+      const int n_c16 = p.C / 32;                          // 16-cell groups per part
+      for (int i = wg; i < 2 * n_c16; i += EPI_WG) {
+        const int prt = i >= n_c16 ? 1 : 0, c = (i - prt * n_c16) * 16;
+        const uint4* src = reinterpret_cast<const uint4*>(row + prt * part) + c / 4;
+        uint4 a = z, b = z, c4 = z, d = z;
+        if (qvalid) { a = __ldg(src); b = __ldg(src + 1); c4 = __ldg(src + 2); d = __ldg(src + 3); }
+        tmem_st16u(tmem_base + ((uint32_t)(lg * 32) << 16) + (prt ? ALO_COL : AHI_COL) + c, a, b, c4, d);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_bar);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(map_to_rank(smem_u32(a_bar), 0)); else mbar_arrive(a_bar);
+      }
     }
     TopK<K> top;
     top.init();
     int buf = 0;
     uint32_t tph0 = 0, tph1 = 0;
     int box_seq = 0;
-    const int row = wg;                                  // the key row of every box this warpgroup owns
-    const bool row_ok = qvalid && row < p.BH;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(row * 16);
+    const int n_rows = (p.BH + EPI_WG - 1) / EPI_WG;       // key rows of a box per warpgroup: wg, wg + 4
+    const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16);
     for (int e = e_hi - 1; e >= e_lo; --e) {           // newest memory frame first: thresholds rise early
-      const int raw = p.mem_feat[e];
-      const bool masked = !(raw & FGVC_MEM_UNMASKED);
+      const int raw = p.ent[e];
+      const bool masked = WIN || !(raw & FGVC_MEM_UNMASKED);
       const int li = masked ? 0 : 1;
       const int nb = nbox[li];
-      const int pos_base = (e - job.mem_begin) * p.n_pix;
-      for (int b = 0; b < nb; ++b) {
-        const uint32_t bb = boxes[li * T16_MAX_BOXES + b];
-        const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
-        const int ky = by + row;
-        // 16-bit interval mask of the in-mask, in-image keys of this key row
-        uint32_t bits = 0;
-        if (row_ok && ky < p.H) {
-          int lo = 0, hi = p.W - 1;
-          if (masked) {
-            const int ady = abs(ky - qy);
-            const int hw = ady <= p.reach ? halfw[ady] : -1;
-            lo = hw < 0 ? 1 : max(qx - hw, 0);
-            hi = hw < 0 ? 0 : min(qx + hw, p.W - 1);
-          }
-          lo = max(lo - bx, 0);
-          hi = min(hi - bx, 15);
-          if (hi >= lo) bits = (2u << hi) - (1u << lo);
+      int upos_e, cy = qy, cx = qx;
+      if (WIN) {
+        upos_e = qvalid ? e - p.job.mem_begin : -1;
+        // this lane's window centre in this memory entry: scale * (coarse arg-max key)   (local_attention.py:835-845)
+        if (qvalid) {
+          const int bq = max(__ldg(p.best + (int64_t)(e - p.job.mem_begin) * nq_c + qy * p.WQ + qx), 0) % nq_c;
+          cy = (bq / p.WQ) * p.scale;
+          cx = (bq % p.WQ) * p.scale;
         }
-        const bool dump = p.dbg != nullptr && box_seq < p.dbg_max_boxes && row < p.BH;
-        const bool doit = (__any_sync(0xffffffffu, bits != 0) || dump) && !(p.exp_flags & 2);    // warp-uniform
+      } else if (p.tgroups) {
+        upos_e = qvalid ? p.upos[4 * e + jm] : -1;     // warp-uniform up to the image border
+      } else {
+        upos_e = qvalid ? e - tg.u_begin : -1;
+      }
+      const bool mine = upos_e >= 0;                       // does this lane's job have this memory entry at all?
+      const int pos_base = upos_e * p.n_pix;
+      for (int b = 0; b < nb; ++b) {
+        const uint32_t bb = boxes[li * MAX_BOXES + b];
+        const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
+        // 16-bit interval masks of the in-mask, in-image keys of this warpgroup's key rows
+        uint32_t bits[2] = {0u, 0u};
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = wg + EPI_WG * rr;
+          const int ky = by + row;
+          if (rr < n_rows && row < p.BH && mine && ky < p.H) {
+            int lo = 0, hi = p.W - 1;
+            if (masked) {
+              const int ady = abs(ky - cy);
+              int hw;
+              if (WIN) hw = ady <= p.rf ? p.rf : -1;
+              else hw = ady <= p.reach ? halfw[ady] : -1;
+              lo = hw < 0 ? 1 : max(cx - hw, 0);
+              hi = hw < 0 ? 0 : min(cx + hw, p.W - 1);
+            }
+            lo = max(lo - bx, 0);
+            hi = min(hi - bx, 15);
+            if (hi >= lo) bits[rr] = (2u << hi) - (1u << lo);
+          }
+        }
+        const bool dump = !WIN && p.dbg != nullptr && box_seq < p.dbg_max_boxes;
+        bool doit[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+          doit[rr] = rr < n_rows && (__any_sync(0xffffffffu, bits[rr] != 0) || (dump && wg + EPI_WG * rr < p.BH)) &&
+                     !(p.exp_flags & 2);                   // warp-uniform
         mbar_wait_sleep(tfull_bar + buf, buf ? tph1 : tph0);
         tc_fence_after();
-        uint32_t r1[16], r2[16];
-        if (doit) {
-          const uint32_t taddr = lane_base + (uint32_t)(buf * 128);
-          tmem_ld16_issue(taddr, r1);
-          tmem_ld16_issue(taddr + (uint32_t)N, r2);
-          tmem_ld_wait(r1);
-          reg_fence16(r2);
-        }
+        uint32_t r0[16], r1[16];
+        const uint32_t taddr = lane_base + (uint32_t)(buf * 128 + wg * 16);
+        if (doit[0]) tmem_ld16_issue(taddr, r0);
+        if (doit[1]) tmem_ld16_issue(taddr + 16 * EPI_WG, r1);
+        if (doit[0]) tmem_ld_wait(r0);
+        if (doit[1]) { if (doit[0]) reg_fence16(r1); else tmem_ld_wait(r1); }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + buf);    // accumulator is in registers: hand the tile back
+        if (lane == 0) {                                   // accumulator is in registers: hand the tile back
+          if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_l1 : tempty_l0); else mbar_arrive(tempty_bar + buf);
+        }
         if (buf) tph1 ^= 1; else tph0 ^= 1;
         buf ^= 1;
-        if (doit) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          if (!doit[rr]) continue;
+          const uint32_t* r = rr ? r1 : r0;
+          const int row = wg + EPI_WG * rr;
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r2[j]), FGVC_F16_LO_INV, __uint_as_float(r1[j]));
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           if (dump) {
             float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = v[j];
-            if (p.dbg_meta != nullptr && m == 0 && wg == 0) {
+            for (int j = 0; j < 16; ++j) d[j] = v[j] * FGVC_F16_ACC_INV;
+            if (p.dbg_meta != nullptr && m == 0 && row == 0) {
               p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
               p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
             }
           }
-          // candidates = in-mask elements above the running K-th value
+          // candidates = in-mask elements above the running K-th value (values stay in accumulator units, x256)
           const float thr0 = (p.exp_flags & 1) ? INFINITY : top.thr();
           uint32_t cand = 0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
-          cand &= bits;
+          cand &= bits[rr];
           // Insert candidates in warp-wide rounds: in every round each lane that still has a
           // candidate takes its next one, so a round serves ~4 lanes at once instead of one
           // divergent insertion per (lane, element).
-          const int kbase = pos_base + ky * p.W + bx;
+          const int kbase = pos_base + (by + row) * p.W + bx;
           while (__any_sync(0xffffffffu, cand != 0)) {
             if (cand) {
               const int j = __ffs(cand) - 1;
@@ -387,39 +576,44 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
       }
     }
     // ---- merge the partial lists of the warpgroups through the (now idle) ring
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * T16_EPI_WG) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     float* mv = reinterpret_cast<float*>(ring);
-    int* mi = reinterpret_cast<int*>(ring + T16_EPI_WG * 128 * K * 4);
+    int* mi = reinterpret_cast<int*>(ring + EPI_WG * 128 * K * 4);
     if (wg > 0) {
 #pragma unroll
       for (int i = 0; i < K; ++i) { mv[(wg * 128 + m) * K + i] = top.v[i]; mi[(wg * 128 + m) * K + i] = top.id[i]; }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * T16_EPI_WG) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     if (wg == 0 && qvalid) {
-      for (int w2 = 1; w2 < T16_EPI_WG; ++w2)
+      for (int w2 = 1; w2 < EPI_WG; ++w2)
         for (int i = 0; i < K; ++i) {
           const float v = mv[(w2 * 128 + m) * K + i];
           if (!(v > top.thr())) break;
           top.push(v, mi[(w2 * 128 + m) * K + i]);
         }
-      const int q = qy * p.W + qx;
-      const int64_t o = (((int64_t)blockIdx.z * p.groups + g) * p.n_pix + q) * p.k_out;
+      const int q = qy * qW + qx;
+      int64_t o;
+      if (WIN) o = ((int64_t)q * ((p.job.mem_end - p.job.mem_begin) * p.chunks) + (blockIdx.y * p.chunks + blockIdx.z)) * p.k_out;
+      else o = (((int64_t)jb * p.lists_per_job + og) * p.n_pix + q) * p.k_out;
 #pragma unroll
       for (int i = 0; i < K; ++i)
-        if (i < p.k_out) { p.tv[o + i] = top.v[i]; p.ti[o + i] = top.id[i]; }
+        if (i < p.k_out) { p.tv[o + i] = top.v[i] * FGVC_F16_ACC_INV; p.ti[o + i] = top.id[i]; }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------ host
-// 5-D map over feat16[slot][part][H][W][C]; box = (64 channels, 16, bh, both parts, 1), 128B swizzle
-static int make_map16(CUtensorMap* map, const void* bank, int n_slots, int H, int W, int C, int bh) {
+// 5-D map over feat16[slot][part][H][W][C]; box = (64 channels, 16, rows per CTA, both parts, 1), 128B swizzle
+static int make_map16(CUtensorMap* map, const void* bank, int n_slots, int H, int W, int C, int rows) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -428,73 +622,201 @@ static int make_map16(CUtensorMap* map, const void* bank, int n_slots, int H, in
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, 2, (cuuint64_t)n_slots};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                            (cuuint64_t)2 * H * W * C * 2};
-  cuuint32_t box[5] = {64, 16, (cuuint32_t)bh, 2, 1};
+  cuuint32_t box[5] = {64, 16, (cuuint32_t)rows, 2, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(bank), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (f16) failed with %d (H=%d W=%d C=%d bh=%d)", (int)r, H, W, C, bh);
+    set_error("cuTensorMapEncodeTiled (f16) failed with %d (H=%d W=%d C=%d rows=%d)", (int)r, H, W, C, rows);
     return FGVC_ERR_CUDA;
   }
   return FGVC_OK;
 }
 
-bool tc16_supported(int H, int W, int C, int K) {
-  return C % 64 == 0 && C >= 64 && C <= 256 && K >= 1 && K <= 16 && H >= 1 && W >= 1;
-}
-
-// all MMAs are TS-form: a box costs ~N plus a small fixed hand-shake
-static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 24); }
-static int pick_bh16(int rows) {
-  int best = T16_MAX_BH;
-  for (int bh = T16_MAX_BH - 1; bh >= 1; --bh)
+// all MMAs are TS-form: a box costs ~N plus a small fixed hand-shake.  Pair tiles stage BH / 2 rows per CTA: BH even.
+static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 12); }
+static int pick_bh16(int rows, int ncta) {
+  const int max_bh = MAX_NC / 16 * ncta;
+  int best = max_bh;
+  for (int bh = max_bh - ncta; bh >= ncta; bh -= ncta)
     if (box_cost16(rows, bh) < box_cost16(rows, best)) best = bh;
   return best;
 }
 
-template <int K>
-static int launch_tc16(const CUtensorMap& mk, const void* bank, const Tc16Params& p, dim3 grid, cudaStream_t st) {
-  FGVC_CUDA(cudaFuncSetAttribute(affinity_topk_tc16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 T16_SMEM_BYTES));
-  affinity_topk_tc16_kernel<K><<<grid, T16_THREADS, T16_SMEM_BYTES, st>>>(mk, reinterpret_cast<const __half*>(bank), p);
+template <int K, int NCTA, bool WIN>
+static int launch_k(const CUtensorMap& mk, const void* bank, const Params& p, dim3 grid, cudaStream_t st) {
+  auto kern = affinity_topk_tc16_kernel<K, NCTA, WIN>;
+  FGVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FGVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mk, reinterpret_cast<const __half*>(bank), p));
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
+}
+template <int NCTA, bool WIN>
+static int launch_by_k(const CUtensorMap& mk, const void* bank, const Params& p, dim3 grid, int K, cudaStream_t st) {
+  if (K <= 4) return launch_k<4, NCTA, WIN>(mk, bank, p, grid, st);
+  if (K <= 10) return launch_k<10, NCTA, WIN>(mk, bank, p, grid, st);
+  return launch_k<16, NCTA, WIN>(mk, bank, p, grid, st);
+}
+
+// pixel block of one job for `rows_per_job` tile rows: as square as the count allows, orientation by halo cost
+static void block_shape(int H, int W, int reach, int rows_per_job, int ncta, int* QH, int* QW, int* BH) {
+  auto halo_cost = [&](int qh, int qw) {
+    int rows = min(H, qh + 2 * reach), cols = min(W, qw + 2 * reach);
+    double tiles = (double)cdiv(H, qh) * cdiv(W, qw);
+    return tiles * box_cost16(rows, pick_bh16(rows, ncta)) * cdiv(cols, 16);
+  };
+  int a = 16, b = 16;
+  switch (rows_per_job) {
+    case 256: a = 16; b = 16; break;
+    case 128: a = 16; b = 8; break;
+    case 64: a = 8; b = 8; break;
+    default: a = 8; b = 4; break;      // 32
+  }
+  if (a != b && halo_cost(b, a) < halo_cost(a, b)) { int t = a; a = b; b = t; }
+  *QH = a; *QW = b;
+  *BH = pick_bh16(min(H, a + 2 * reach), ncta);
+}
+
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+}  // namespace tc16
+
+bool tc16_supported(int H, int W, int C, int K) {
+  return C % 64 == 0 && C >= 64 && C <= 256 && K >= 1 && K <= 16 && H >= 1 && W >= 1;
+}
+
+// CTA pairs need >= 2 key rows per box and are only worth their wider tiles on maps with enough tiles
+static bool use_pairs(int H, int W, int jobs_per_tile) {
+  const int force = getenv("FGVC_TC16_PAIR") ? atoi(getenv("FGVC_TC16_PAIR")) : -1;   // experiments / tests
+  if (force == 0 || force == 1) return force == 1;
+  (void)jobs_per_tile;
+  return H >= 2 && (int64_t)H * W >= 1024;
+}
+
+// tile = jobs_per_tile jobs x (128 * ncta / jobs_per_tile) pixels.  Exposed so that the host can cost the packings
+// before building the tables.
+void packed_tile_shape(int H, int W, int reach, int jobs_per_tile, int* QH, int* QW, int* BH, int* ncta_out) {
+  const int ncta = use_pairs(H, W, jobs_per_tile) ? 2 : 1;
+  tc16::block_shape(H, W, reach, 128 * ncta / jobs_per_tile, ncta, QH, QW, BH);
+  if (ncta_out) *ncta_out = ncta;
+}
+
+static int launch_k1(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_z,
+                     const fgvc_tile_group* tgroups, const int32_t* ent, const int32_t* upos, int jobs_per_tile,
+                     int radius, int mode, int K, int lists_per_job, int split, float* tv, int32_t* ti, float* dbg,
+                     int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st) {
+  using namespace tc16;
+  Params p = {};
+  p.H = H; p.W = W; p.C = C; p.n_pix = H * W;
+  p.radius = radius; p.mode = mode; p.reach = mask_reach(radius, mode);
+  int ncta = 1;
+  packed_tile_shape(H, W, p.reach, jobs_per_tile, &p.QH, &p.QW, &p.BH, &ncta);
+  if (dbg) {                    // the debug dump describes single-CTA tiles
+    ncta = 1;
+    block_shape(H, W, p.reach, 128 / jobs_per_tile, 1, &p.QH, &p.QW, &p.BH);
+  }
+  static const int force_bh = getenv("FGVC_TC16_BH") ? atoi(getenv("FGVC_TC16_BH")) : 0;   // timing experiments only
+  if (force_bh >= ncta && force_bh <= MAX_NC / 16 * ncta && force_bh % ncta == 0) p.BH = force_bh;
+  p.qw_shift = ilog2(p.QW);
+  p.lpj_shift = ilog2(128 * ncta / jobs_per_tile);
+  p.lists_per_job = lists_per_job; p.split = split; p.k_out = K;
+  p.tiles_x = cdiv(W, p.QW);
+  p.jobs = jobs; p.tgroups = tgroups; p.ent = ent; p.upos = upos; p.tv = tv; p.ti = ti;
+  p.dbg = dbg; p.dbg_meta = dbg_meta; p.dbg_max_boxes = dbg_max_boxes;
+  static const int exp_flags = getenv("FGVC_TC16_EXP") ? atoi(getenv("FGVC_TC16_EXP")) : 0;   // perf experiments only
+  p.exp_flags = exp_flags;
+  FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 f16 engine: radius %d too large", radius);
+  if (cdiv(H, p.BH) * cdiv(W, 16) > MAX_BOXES || H >= 65536 || W >= 65536) {
+    set_error("tcgen05 f16 engine: a %dx%d map has more than %d key boxes", H, W, MAX_BOXES);
+    return FGVC_ERR_UNSUPPORTED;      // AUTO falls back to the CUDA-core engine
+  }
+  CUtensorMap mk;
+  int rc = make_map16(&mk, bank, n_slots, H, W, C, p.BH / ncta);
+  if (rc) return rc;
+  dim3 grid(cdiv(H, p.QH) * p.tiles_x * ncta, split, n_z);
+  if (ncta == 2) return launch_by_k<2, false>(mk, bank, p, grid, K, st);
+  return launch_by_k<1, false>(mk, bank, p, grid, K, st);
 }
 
 int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
                               float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st) {
-  Tc16Params p;
-  p.H = H; p.W = W; p.C = C; p.n_pix = H * W;
-  p.radius = radius; p.mode = mode; p.reach = mask_reach(radius, mode);
-  const int reach = p.reach;
-  auto halo_cost = [&](int qh, int qw) {
-    int rows = min(H, qh + 2 * reach), cols = min(W, qw + 2 * reach);
-    double tiles = (double)cdiv(H, qh) * cdiv(W, qw);
-    return tiles * box_cost16(rows, pick_bh16(rows)) * cdiv(cols, 16);
-  };
-  if (halo_cost(16, 8) < halo_cost(8, 16)) { p.QH = 16; p.QW = 8; p.qw_shift = 3; }
+  return launch_k1(bank, n_slots, H, W, C, jobs, n_jobs, nullptr, mem_feat, nullptr, 1, radius, mode, K, groups, groups,
+                   tv, ti, dbg, dbg_meta, dbg_max_boxes, st);
+}
+
+int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs,
+                                     const fgvc_tile_group* tgroups, int n_tgroups, const int32_t* uent,
+                                     const int32_t* upos, int jobs_per_tile, int radius, int mode, int K, int groups,
+                                     int split, float* tv, int32_t* ti, cudaStream_t st) {
+  FGVC_CHECK_ARG(jobs_per_tile == 1 || jobs_per_tile == 2 || jobs_per_tile == 4,
+                 "packed tcgen05 engine: jobs_per_tile=%d must be 1, 2 or 4", jobs_per_tile);
+  FGVC_CHECK_ARG(split >= 1 && groups % split == 0, "packed tcgen05 engine: groups=%d is not a multiple of split=%d",
+                 groups, split);
+  return launch_k1(bank, n_slots, H, W, C, jobs, n_tgroups, tgroups, uent, upos, jobs_per_tile, radius, mode, K, groups,
+                   split, tv, ti, nullptr, nullptr, 0, st);
+}
+
+// ------------------------------------------------------------------------------ window mode (K2 fine stage)
+// masked_attention_efficient_c2f (local_attention.py:721-880): every coarse query looks, in every memory frame, at
+// the (2 rf + 1)^2 window of the FINE key map centred at scale * (coarse arg-max key) -- a data-dependent centre per
+// (query, frame).  Same engine with three changes of geometry: a tile = 128 COARSE queries whose operand rows are
+// the fine query features at the strided positions; one CTA = (tile, memory entry, chunk of that entry's boxes),
+// the boxes covering the bounding rectangle of the tile's 128 window centres grown by rf; the mask of a lane is
+// its own window around ITS centre of this entry.  Zero-padded window positions (affinity 0, value 0 in the
+// reference's F.unfold) are counted analytically and inserted by the tail kernel (c2f.cu).
+bool c2f_window_supported(int Hf, int Wf, int Cf, int K, int n_mem) {
+  return tc16_supported(Hf, Wf, Cf, K) && n_mem >= 1 && n_mem <= tc16::TW_MAX_MEM && Hf < 65536 && Wf < 65536 &&
+         (int64_t)n_mem * Hf * Wf < (1ll << 31);
+}
+
+// how many CTAs share one (tile, entry): fill the chip, at most 4 (the tail merges n_mem * chunks lists per query)
+int c2f_window_chunks(int Hc, int Wc, int n_mem) {
+  const long tiles = (long)cdiv(Hc, 8) * cdiv(Wc, 16);
+  long c = 148 / (tiles * n_mem > 0 ? tiles * n_mem : 1);
+  return (int)(c < 1 ? 1 : (c > 4 ? 4 : c));
+}
+
+// fine stage of c2f as a window-mode K1: top-K lists tv / ti [Hc * Wc][n_mem * chunks][K] over the in-window, in-image
+// fine keys (idx = memory position * Hf * Wf + fine key pixel).  best: [n_mem][Hc * Wc] coarse arg-max keys.
+int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
+                           const fgvc_job& job, const int32_t* mem_feat, const int32_t* best, int rf, int K, int chunks,
+                           float* tv, int32_t* ti, cudaStream_t st) {
+  using namespace tc16;
+  Params p = {};
+  p.H = Hf; p.W = Wf; p.C = Cf; p.n_pix = Hf * Wf;
+  p.HQ = Hc; p.WQ = Wc; p.scale = scale; p.rf = rf;
+  // coarse tile 8 x 16 or 16 x 8: whichever leaves fewer idle lanes on this grid
+  const long waste_a = (long)cdiv(Hc, 8) * cdiv(Wc, 16), waste_b = (long)cdiv(Hc, 16) * cdiv(Wc, 8);
+  if (waste_b < waste_a) { p.QH = 16; p.QW = 8; p.qw_shift = 3; }
   else { p.QH = 8; p.QW = 16; p.qw_shift = 4; }
-  p.BH = pick_bh16(min(H, p.QH + 2 * reach));
-  p.groups = groups; p.k_out = K;
-  p.tiles_x = cdiv(W, p.QW);
-  p.jobs = jobs; p.mem_feat = mem_feat; p.tv = tv; p.ti = ti;
-  p.dbg = dbg; p.dbg_meta = dbg_meta; p.dbg_max_boxes = dbg_max_boxes;
-  static const int exp_flags = getenv("FGVC_TC16_EXP") ? atoi(getenv("FGVC_TC16_EXP")) : 0;   // perf experiments only
-  p.exp_flags = exp_flags;
-  FGVC_CHECK_ARG(p.reach + 1 <= 128, "tcgen05 f16 engine: radius %d too large", radius);
-  if (cdiv(H, p.BH) * cdiv(W, 16) > T16_MAX_BOXES || H >= 65536 || W >= 65536) {
-    set_error("tcgen05 f16 engine: a %dx%d map has more than %d key boxes", H, W, T16_MAX_BOXES);
-    return FGVC_ERR_UNSUPPORTED;      // AUTO falls back to the CUDA-core engine
+  p.lpj_shift = 7;
+  p.BH = MAX_NC / 16;
+  p.k_out = K;
+  p.chunks = chunks;
+  p.tiles_x = cdiv(Wc, p.QW);
+  p.job = job; p.ent = mem_feat; p.best = best; p.tv = tv; p.ti = ti;
+  // worst case (scattered arg-max keys): the entry lists every box of the frame
+  if ((int64_t)cdiv(Hf, p.BH) * cdiv(Wf, 16) > 2 * MAX_BOXES) {
+    set_error("c2f window engine: a %dx%d map exceeds %d key boxes", Hf, Wf, 2 * MAX_BOXES);
+    return FGVC_ERR_UNSUPPORTED;
   }
   CUtensorMap mk;
-  int rc = make_map16(&mk, bank, n_slots, H, W, C, p.BH);
+  int rc = make_map16(&mk, fine_bank, n_slots, Hf, Wf, Cf, p.BH);
   if (rc) return rc;
-  dim3 grid(cdiv(H, p.QH) * p.tiles_x, groups, n_jobs);
-  if (K <= 4) return launch_tc16<4>(mk, bank, p, grid, st);
-  if (K <= 10) return launch_tc16<10>(mk, bank, p, grid, st);
-  return launch_tc16<16>(mk, bank, p, grid, st);
+  dim3 grid(cdiv(Hc, p.QH) * p.tiles_x, job.mem_end - job.mem_begin, chunks);
+  return launch_by_k<1, true>(mk, fine_bank, p, grid, K, st);
 }
 
 }  // namespace fgvc

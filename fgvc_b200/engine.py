@@ -13,7 +13,18 @@ import torch
 from . import _lib
 from ._lib import Job, call, ptr, stream_ptr
 
-NUM_SMS = 148
+_NUM_SMS = {}
+
+
+def num_sms(device=None):
+    """SM count of ``device`` (grid sizing of the host-side planners); 148 on a B200."""
+    idx = torch.device(device).index if device is not None and torch.device(device).index is not None \
+        else (torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    if idx < 0:
+        return 148
+    if idx not in _NUM_SMS:
+        _NUM_SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _NUM_SMS[idx]
 
 
 def pad4(n):
@@ -29,7 +40,7 @@ def default_split(C):
 class FeatureBank:
     """feat[slot][2][H*W][C]: L2-normalised, pixel-major two-term split (K0 output).
     ``split='tf32'``: fp32 cells, hi = tf32(x), lo = x - hi (3xTF32 engine);
-    ``split='f16'``: fp16 cells, hi = fp16(x), lo = fp16((x - hi) * 2^11) (fp16 three-term engine)."""
+    ``split='f16'``: fp16 cells, X = 16 x, hi = fp16(X), lo = fp16(X - hi) (fp16 three-term engine)."""
 
     def __init__(self, n_slots, C, H, W, device, split=None):
         _lib.require_cuda()
@@ -41,12 +52,12 @@ class FeatureBank:
         self.fmt = _lib.BANK_F16 if self.split == "f16" else _lib.BANK_TF32
         dt = torch.float16 if self.split == "f16" else torch.float32
         self.buf = torch.empty(n_slots, 2, H * W, C, dtype=dt, device=device)
-        self.unit_rows = True          # until a frame is loaded without normalisation (prefilter engine needs it)
+        self.unit_rows = True          # until a frame is loaded without normalisation
 
     def dense(self):
         """fp32 [slot, H*W, C] view of what the split encodes (tests / diagnostics)."""
         if self.split == "f16":
-            return self.buf[:, 0].float() + self.buf[:, 1].float() / 2048.0
+            return (self.buf[:, 0].float() + self.buf[:, 1].float()) / 16.0
         return self.buf[:, 0] + self.buf[:, 1]
 
     def load(self, src, first_slot, n_frames, frame_stride, chan_stride, normalize=True):
@@ -147,49 +158,63 @@ class JobTable:
     def host_job(self, i):
         return Job(*self.jobs[i])
 
-    def union_sizes(self, j0, j1, J):
-        """sizes of the union memory lists when jobs [j0, j1) are packed J at a time (cost model)."""
+    def _tile_groups(self, j0, j1, J, aligned):
+        """[(out_group, [job indices])]: J consecutive jobs per group; ``aligned``: one set of groups per class a of
+        memory frames (slot % J == a), the jobs grouped with phase a (query slots a+1 .. a+J together) so that a
+        sliding memory window is used by all J jobs of a group or by none."""
+        if not aligned:
+            return [(0, list(range(a, min(a + J, j1)))) for a in range(j0, j1, J)]
         out = []
-        for a in range(j0, j1, J):
-            keys = set()
-            for i in range(a, min(a + J, j1)):
-                seen = {}
-                for raw in self.mem_feat[self.jobs[i][1]:self.jobs[i][2]]:
-                    occ = seen.get(raw, 0)
-                    seen[raw] = occ + 1
-                    keys.add((raw, occ))
-            out.append(len(keys))
+        for a in range(J):
+            groups = {}
+            for i in range(j0, j1):
+                groups.setdefault((self.jobs[i][0] - a - 1) // J, []).append(i)
+            out.extend((a, groups[g]) for g in sorted(groups))
         return out
 
-    def packed(self, j0, j1, J, device):
-        """Tile groups of J consecutive jobs of [j0, j1) for fgvc_affinity_topk_packed: (groups [n,8] int32,
-        union entries [U] int32, union positions [U,4] int32) on ``device``.  A memory list is a multiset (frame 0
-        twice while t <= precede_frames): the k-th occurrence of a frame in one job is matched with the k-th
-        occurrence in the others.  Union entries are ordered oldest frame first -- the kernel walks them backwards."""
-        key = (j0, j1, J, str(device))
+    def sequential(self, j0, j1):
+        """jobs [j0, j1) are consecutive query frames (what the aligned packing assumes)"""
+        return all(self.jobs[i + 1][0] == self.jobs[i][0] + 1 for i in range(j0, j1 - 1))
+
+    def _group_table(self, members, J, cls):
+        """union entries of a tile group: {(raw entry, occurrence): [position in member i's own list or -1] * 4}"""
+        table = {}
+        for li, i in enumerate(members):
+            seen = {}
+            b, e = self.jobs[i][1], self.jobs[i][2]
+            for pos, raw in enumerate(self.mem_feat[b:e]):
+                occ = seen.get(raw, 0)
+                seen[raw] = occ + 1
+                if cls is None or (raw & ~_lib.MEM_UNMASKED) % J == cls:
+                    table.setdefault((raw, occ), [-1, -1, -1, -1])[li] = pos
+        return table
+
+    def union_sizes(self, j0, j1, J, aligned=False):
+        """sizes of the union memory lists of the tile groups of jobs [j0, j1) (cost model)."""
+        return [len(self._group_table(m, J, a if aligned else None)) for a, m in self._tile_groups(j0, j1, J, aligned)]
+
+    def packed(self, j0, j1, J, device, aligned=False):
+        """Tile groups of jobs [j0, j1) for fgvc_affinity_topk_packed: (groups [n,8] int32, union entries [U] int32,
+        union positions [U,4] int32) on ``device``.  A memory list is a multiset (frame 0 twice while
+        t <= precede_frames): the k-th occurrence of a frame in one job is matched with the k-th occurrence in the
+        others.  Union entries are ordered oldest frame first -- the kernel walks them backwards."""
+        key = (j0, j1, J, bool(aligned), str(device))
         hit = self._packed.get(key)
         if hit is not None:
             return hit
         groups, uent, upos = [], [], []
-        for a in range(j0, j1, J):
-            members = list(range(a, min(a + J, j1)))
-            table = {}
-            for li, i in enumerate(members):
-                seen = {}
-                b, e = self.jobs[i][1], self.jobs[i][2]
-                for pos, raw in enumerate(self.mem_feat[b:e]):
-                    occ = seen.get(raw, 0)
-                    seen[raw] = occ + 1
-                    table.setdefault((raw, occ), [-1, -1, -1, -1])[li] = pos
+        for cls, members in self._tile_groups(j0, j1, J, aligned):
+            assert len(members) <= 4
+            table = self._group_table(members, J, cls if aligned else None)
             order = sorted(table, key=lambda k: (k[0] & ~_lib.MEM_UNMASKED, 0 if (k[0] & _lib.MEM_UNMASKED) else 1, k[1]))
             u0 = len(uent)
             for k in order:
                 uent.append(k[0])
                 upos.append(table[k])
-            groups.append(members + [-1] * (4 - len(members)) + [len(members), u0, len(uent), 0])
+            groups.append(members + [-1] * (4 - len(members)) + [len(members), u0, len(uent), cls])
         out = (torch.tensor(groups, dtype=torch.int32).reshape(-1, 8).to(device),
-               torch.tensor(uent, dtype=torch.int32).to(device),
-               torch.tensor(upos, dtype=torch.int32).reshape(-1, 4).to(device))
+               torch.tensor(uent if uent else [0], dtype=torch.int32).to(device),
+               torch.tensor(upos if upos else [[-1] * 4], dtype=torch.int32).reshape(-1, 4).to(device))
         self._packed[key] = out
         return out
 
@@ -202,7 +227,7 @@ def pick_groups(n_jobs, H, W, max_mem, max_groups=4):
     ctas = n_jobs * (-(-H // 8)) * (-(-W // 16))          # 128-query tiles (8x16 or 16x8 pixels)
     best, best_cost = 1, None
     for g in range(1, max(1, min(max_groups, max_mem)) + 1):
-        rounds = -(-ctas * g // NUM_SMS)
+        rounds = -(-ctas * g // num_sms())
         cost = rounds / g + 0.02 * (g - 1)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = g, cost
@@ -216,10 +241,10 @@ def plan_chunks(n_jobs, tiles, copy_ratio=0.75, launch_cost=0.4):
     programme over cut positions minimising the finish time; unit = compute time of one job at full
     efficiency, ``copy_ratio`` = copy time of one frame in that unit, ``launch_cost`` = per-chunk overhead
     (K0 + tail launches, pipeline fill)."""
-    jobs_per_round = NUM_SMS / float(tiles)
+    jobs_per_round = num_sms() / float(tiles)
 
     def compute(n):
-        return -(-n * tiles // NUM_SMS) * jobs_per_round + launch_cost
+        return -(-n * tiles // num_sms()) * jobs_per_round + launch_cost
 
     INF = float("inf")
     best = [(INF, None)] * (n_jobs + 1)
@@ -244,7 +269,7 @@ def plan_overlap_chunks(n_jobs, tiles, max_chunks=6):
     costs no extra round compared with one launch, so that the gather chain of chunk i (second stream)
     can overlap K1 of chunk i+1 for free.  Falls back to a single launch."""
     def rounds(n):
-        return -(-n * tiles // NUM_SMS)
+        return -(-n * tiles // num_sms())
 
     single = rounds(n_jobs)
     best = [(0, n_jobs)]
@@ -269,7 +294,6 @@ class TopKLists:
         self.idx = torch.empty(n_jobs, groups, n_query, K, dtype=torch.int32, device=device)
 
 
-_WORKSPACES = {}
 _CHAIN_WS = {}
 
 
@@ -279,39 +303,42 @@ def _ws_key(dev):
     return (idx, torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _workspace(dev, nbytes):
-    """Caller-owned scratch of the prefilter engine, one per (device, stream), grown on demand.  Work on
-    one stream is ordered, so consecutive K1 launches can share it."""
-    key = _ws_key(dev)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        _WORKSPACES[key] = ws
-    return ws
-
-
 _COVER = {}
+
+
+def tile_shape(H, W, radius, mode, J):
+    """(QH, QW, BH, ncta) of the fp16 tensor engine for J jobs per tile: pixel block of one job, key-box height, CTAs
+    per tile (2 = CTA pair, 256 tile rows)."""
+    import ctypes as ct
+    qh, qw, bh, nc = ct.c_int32(), ct.c_int32(), ct.c_int32(), ct.c_int32()
+    call("fgvc_packed_tile_shape", H, W, int(radius), int(mode), int(J), ct.byref(qh), ct.byref(qw), ct.byref(bh),
+         ct.byref(nc))
+    return qh.value, qw.value, bh.value, nc.value
+
+
+BOX_FIXED = 12        # per-box hand-shake of the engine in key units (csrc/topk_tc16.cu: box_cost16)
+TILE_SETUP = 160      # per (tile, tile group) set-up in key units: barriers, TMEM, query rows, box lists, list merge
 
 
 def _cover_keys(H, W, radius, mode, J):
     """Keys a query tile multiplies (whole key boxes of its radius halo that some query can see), summed over
-    the tiles of a map, for J jobs per tile -- the geometry of csrc/topk_tc16g.cu.  Every tile is a full M = 128
-    MMA, so the tensor work of a launch is  sum over tile groups of |union memory list| x this number."""
-    key = (H, W, radius, mode, J)
+    the tiles of a map, for J jobs per tile -- the geometry of csrc/topk_tc16.cu.  Every tile is a full M = 128
+    (x 2 for CTA pairs) MMA, so the tensor work of a launch is  sum over tile groups of |union memory list| x this
+    number x tile rows."""
+    env = os.environ.get("FGVC_TC16_PAIR", "")
+    key = (H, W, radius, mode, J, env)
     if key in _COVER:
         return _COVER[key]
-    import ctypes as ct
-    qh, qw, bh = ct.c_int32(), ct.c_int32(), ct.c_int32()
-    call("fgvc_packed_tile_shape", H, W, int(radius), int(mode), int(J), ct.byref(qh), ct.byref(qw), ct.byref(bh))
-    QH, QW, BH = qh.value, qw.value, bh.value
+    QH, QW, BH, ncta = tile_shape(H, W, radius, mode, J)
     reach = radius - 1 if mode == _lib.MASK_CIRCLE else radius
 
     def seen(dy, dx):
         return dy * dy + dx * dx < radius * radius if mode == _lib.MASK_CIRCLE else (dy <= radius and dx <= radius)
 
-    total = keys = 0
+    total = keys = tiles = 0
     for qy0 in range(0, H, QH):
         for qx0 in range(0, W, QW):
+            tiles += 1
             y_lo, y_hi = max(0, qy0 - reach), min(H - 1, qy0 + QH - 1 + reach)
             x_lo, x_hi = max(0, qx0 - reach), min(W - 1, qx0 + QW - 1 + reach)
             qy1, qx1 = min(H - 1, qy0 + QH - 1), min(W - 1, qx0 + QW - 1)
@@ -320,35 +347,47 @@ def _cover_keys(H, W, radius, mode, J):
                 for bx in range(x_lo, x_hi + 1, 16):
                     dx = max(0, bx - qx1, qx0 - min(W - 1, bx + 15))
                     if seen(dy, dx):
-                        total += 16 * BH + 24          # + the fixed per-box hand-shake (box_cost16)
+                        total += 16 * BH + BOX_FIXED
                         keys += 16 * BH
-    _COVER[key] = total
-    _COVER[key + ("keys",)] = keys
-    return total
+    _COVER[key] = dict(cost=total, keys=keys, tiles=tiles, rows=128 * ncta)
+    return _COVER[key]
 
 
-def dense_pairs(table, j0, j1, H, W, radius, mode, J):
+def dense_pairs(table, j0, j1, H, W, radius, mode, J, aligned=False):
     """(query row, key) pairs the tensor engine multiplies for jobs [j0, j1) packed J per tile: every tile is a
-    full M = 128 MMA against every key box of its halo, for every entry of the group's union memory list."""
-    _cover_keys(H, W, radius, mode, J)
-    return 128 * _COVER[(H, W, radius, mode, J, "keys")] * sum(table.union_sizes(j0, j1, J))
+    full MMA against every key box of its halo, for every entry of the group's union memory list."""
+    c = _cover_keys(H, W, radius, mode, J)
+    return c["rows"] * c["keys"] * sum(table.union_sizes(j0, j1, J, aligned))
+
+
+def packing_cost(table, j0, j1, H, W, radius, mode, J, aligned=False):
+    """tensor time of one K1 launch in key units x tile rows (the cost model behind pick_packing)."""
+    c = _cover_keys(H, W, radius, mode, J)
+    u = table.union_sizes(j0, j1, J, aligned)
+    return c["rows"] * (sum(u) * c["cost"] + len(u) * c["tiles"] * TILE_SETUP)
 
 
 def pick_packing(table, j0, j1, H, W, radius, mode):
-    """jobs per tile (1, 2 or 4) with the least tensor work for jobs [j0, j1); FGVC_PACK forces it."""
+    """(jobs per tile, aligned) with the least tensor work for jobs [j0, j1).  ``aligned`` = memory frames are
+    divided into J classes by slot index mod J and the query frames of class a are grouped with phase a, so that
+    every job of a tile group uses every memory entry of the group (no wasted rows at the ends of the sliding
+    window); each job then has J partial lists, merged by the gather.  FGVC_PACK = "J" or "Ja" forces it."""
     forced = os.environ.get("FGVC_PACK")
+    seq = table.sequential(j0, j1)
     if forced is not None:
-        return int(forced)
+        return int(forced.rstrip("a")), forced.endswith("a") and seq
     if j1 - j0 < 2:
-        return 1
-    ckey = ("pick", j0, j1, H, W, radius, mode)
+        return 1, False
+    ckey = ("pick", j0, j1, H, W, radius, mode, os.environ.get("FGVC_TC16_PAIR", ""))
     if ckey in table._packed:
         return table._packed[ckey]
-    best, best_cost = 1, None
-    for J in (1, 2, 4):
-        cost = sum(table.union_sizes(j0, j1, J)) * _cover_keys(H, W, radius, mode, J)
-        if best_cost is None or cost < 0.97 * best_cost:      # packing must pay for its extra set-up
-            best, best_cost = J, cost
+    best, best_cost = (1, False), None
+    for J, aligned in ((1, False), (2, False), (4, False), (2, True), (4, True)):
+        if aligned and not seq:
+            continue
+        cost = packing_cost(table, j0, j1, H, W, radius, mode, J, aligned)
+        if best_cost is None or cost < 0.97 * best_cost:      # a more complex packing must pay for itself
+            best, best_cost = (J, aligned), cost
     table._packed[ckey] = best
     return best
 
@@ -393,40 +432,75 @@ def chain_workspace(dev, n_jobs, n_pix, K, flags=0, force=False):
     return ptr(ws), nbytes
 
 
+class K1Plan:
+    """How one K1 launch is tiled: J jobs per query tile, ``aligned`` memory classes (pick_packing), ``split`` parts
+    per tile group (load balance of short launches).  A job gets ``lists_per_job`` partial top-k lists."""
+
+    def __init__(self, J=1, aligned=False, split=1):
+        self.J, self.aligned, self.split = int(J), bool(aligned), int(split)
+
+    @property
+    def lists_per_job(self):
+        return (self.J if self.aligned else 1) * self.split
+
+    def __repr__(self):
+        return f"K1Plan(J={self.J}, aligned={self.aligned}, split={self.split})"
+
+
+def tensor16_ok(bank, K, engine):
+    return engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05) and bank.fmt == _lib.BANK_F16 and \
+        bool(_lib.load().fgvc_tc_supported(bank.fmt, bank.H, bank.W, bank.C, int(K)))
+
+
+def plan_k1(bank, table, radius, K, mask_mode="circle", job_range=None, engine=_lib.ENGINE_AUTO, groups=None, pack=True):
+    """Tiling of a K1 launch over ``job_range`` of ``table``.  ``groups`` fixes the lists per job (no aligned classes)."""
+    j0, j1 = job_range if job_range is not None else (0, len(table))
+    mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
+    J, aligned = 1, False
+    if pack and tensor16_ok(bank, K, engine):
+        J, aligned = pick_packing(table, j0, j1, bank.H, bank.W, int(radius), mode)
+        if groups is not None and aligned:
+            aligned = False
+    if groups is None:
+        groups = 1 if aligned else pick_groups(j1 - j0, bank.H, bank.W, table.max_mem)
+    return K1Plan(J, aligned, groups)
+
+
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
-                  job_range=None, pack=True):
+                  job_range=None, pack=True, plan=None):
     """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch.  ``AUTO``
-    = the exact tensor engine of the bank format, else the CUDA-core engine; ``ENGINE_PREFILTER`` (one fp16
-    tensor MAC per pair + exact rescoring; F16 banks of unit rows) is explicit."""
+    = the tensor engine of the bank format when the shape allows, else the CUDA-core engine.  ``plan`` (plan_k1)
+    fixes the tiling; the lists hold ``plan.lists_per_job`` partial lists per job, merged by the gather."""
     dev = bank.buf.device
     jobs, mem_feat, _ = table.device(dev)
-    if groups is None:
-        groups = pick_groups(len(table), bank.H, bank.W, table.max_mem)
+    j0, j1 = job_range if job_range is not None else (0, len(table))
+    if plan is None:
+        if groups is None and lists is not None:
+            groups = lists.groups
+        plan = plan_k1(bank, table, radius, K, mask_mode, (j0, j1), engine, groups, pack)
+    groups = plan.lists_per_job
     if lists is None:
         lists = TopKLists(len(table), groups, bank.H * bank.W, K, dev)
-    assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table)
+    assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table), (lists.groups, plan)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
-    j0, j1 = job_range if job_range is not None else (0, len(table))
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
-    # fp16 tensor engine: pack J consecutive jobs into one query tile when that saves tensor work (topk_tc16g.cu)
-    if pack and engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05) and bank.fmt == _lib.BANK_F16 and \
-            _lib.load().fgvc_tc_supported(bank.fmt, bank.H, bank.W, bank.C, int(K)):
-        J = pick_packing(table, j0, j1, bank.H, bank.W, int(radius), mode)
-        if J > 1:
-            tg, uent, upos = table.packed(j0, j1, J, dev)
+    # fp16 tensor engine: J consecutive jobs per query tile when that saves tensor work (csrc/topk_tc16.cu)
+    if (plan.J > 1 or plan.aligned) and tensor16_ok(bank, K, engine):
+        tg, uent, upos = table.packed(j0, j1, plan.J, dev, plan.aligned)
+        try:
             call("fgvc_affinity_topk_packed", ptr(bank.buf), bank.n_slots, bank.H, bank.W, bank.C, ptr(jobs), ptr(tg),
-                 int(tg.shape[0]), ptr(uent), ptr(upos), int(J), int(radius), mode, int(K), int(groups),
-                 ptr(lists.val), ptr(lists.idx), stream_ptr())
+                 int(tg.shape[0]), ptr(uent), ptr(upos), int(plan.J), int(radius), mode, int(K), int(groups),
+                 int(plan.split), ptr(lists.val), ptr(lists.idx), stream_ptr())
             return lists
-    ws, ws_bytes = None, 0
-    if engine == _lib.ENGINE_PREFILTER and bank.unit_rows and \
-            _lib.load().fgvc_prefilter_supported(bank.fmt, bank.H, bank.W, bank.C, int(K), int(groups)):
-        ws_bytes = int(_lib.load().fgvc_affinity_topk_workspace_bytes(j1 - j0, int(groups), lists.n_query, int(K)))
-        ws = _workspace(dev, ws_bytes)
-    call("fgvc_affinity_topk_ws", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
+        except _lib.FgvcError as err:
+            # a shape the tensor kernel does not take (e.g. a huge map): AUTO goes on to the un-packed entry point,
+            # which falls back to the CUDA-core engine
+            if err.rc != _lib.ERR_UNSUPPORTED or engine != _lib.ENGINE_AUTO:
+                raise
+    call("fgvc_affinity_topk", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
          ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
          ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),
-         int(engine), int(bool(bank.unit_rows)), ptr(ws) if ws is not None else None, ws_bytes, stream_ptr())
+         int(engine), stream_ptr())
     return lists
 
 
@@ -544,7 +618,10 @@ class MaskClipPropagator:
             mem = memory_frames(t, cfg["precede_frames"], cfg.get("with_first", True))
             self.table.add(t, mem, mem, t, unmasked=len(mem) if nr is None else unmasked_first)
         self.radius = (nr // 2) if nr is not None else 1
-        self.groups = pick_groups(len(self.table), H, W, self.table.max_mem) if T > 1 else 1
+        # the tiling of K1 (jobs per tile, aligned memory classes, parts) is fixed per clip: it sizes the lists
+        self.plan = plan_k1(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
+                            engine=engine_id) if T > 1 else K1Plan()
+        self.groups = self.plan.lists_per_job
         self.lists = TopKLists(max(1, len(self.table)), self.groups, H * W, cfg["topk"], device) if T > 1 else None
         self.table.device(device)
         self.maps = torch.empty(T, L, H, W, dtype=torch.float32, device=device)
@@ -581,7 +658,7 @@ class MaskClipPropagator:
         cfg = self.cfg
         lists = lists or self.lists
         affinity_topk(self.bank, self.table, self.radius, cfg["topk"], cfg.get("mask_mode", "circle"),
-                      groups=lists.groups, engine=self.engine_id, lists=lists, job_range=(j0, j1))
+                      engine=self.engine_id, lists=lists, job_range=(j0, j1), plan=self.plan)
 
     def run(self, feats, onehot0, events=False, want_maps=True):
         """feats [T,C,H,W] fp32 CUDA; onehot0 [L,H,W] fp32 CUDA.  Returns (maps, masks);

@@ -58,9 +58,10 @@ typedef enum fgvc_status {
 
 /* feature-bank formats (both hold an L2-normalised frame as a two-term split, pixel-major):
  *   TF32: fp32 [slot][2][H*W][C], hi = tf32(x), lo = x - hi            -> 3xTF32 tensor engine
- *   F16 : fp16 [slot][2][H*W][C], hi = fp16(x), lo = fp16((x - hi) * 2^11) -> 3-term fp16 tensor
+ *   F16 : fp16 [slot][2][H*W][C], X = 16 x, hi = fp16(X), lo = fp16(X - hi)  -> 3-term fp16 tensor
  *         engine (same 11 + 11 significant bits per operand, twice the MMA depth per instruction,
- *         half the bytes).  Needs C % 64 == 0. */
+ *         half the bytes; the 2^4 scale keeps lo a normal fp16 number so the three products share one
+ *         fp32 accumulator).  Needs C % 64 == 0. */
 typedef enum fgvc_bank_format { FGVC_BANK_TF32 = 0, FGVC_BANK_F16 = 1 } fgvc_bank_format;
 
 typedef enum fgvc_mask_mode { FGVC_MASK_CIRCLE = 0, FGVC_MASK_SQUARE = 1 } fgvc_mask_mode;
@@ -71,13 +72,7 @@ typedef enum fgvc_mask_mode { FGVC_MASK_CIRCLE = 0, FGVC_MASK_SQUARE = 1 } fgvc_
 typedef enum fgvc_engine {
   FGVC_ENGINE_AUTO = 0,
   FGVC_ENGINE_SIMT = 1,
-  FGVC_ENGINE_TCGEN05 = 2,
-  /* F16 bank with UNIT rows (K0 with normalize = 1) only: one fp16 tensor MAC per (query, key) pair finds a
-   * rigorous superset of the top-K (|error| <= 1.25e-3 => band of 2.5e-3 below the K-th value), the superset is
-   * re-scored exactly in fp32 and the exact top-K is taken from it; queries whose superset may be
-   * incomplete are re-done by an exact scan.  Same results as TCGEN05 at a third of the tensor work
-   * (experimental: explicit only, AUTO never picks it).  Needs the workspace of fgvc_affinity_topk_ws. */
-  FGVC_ENGINE_PREFILTER = 3
+  FGVC_ENGINE_TCGEN05 = 2
 } fgvc_engine;
 
 /* One propagation job = one query frame and its memory list (a multiset of frames:
@@ -99,7 +94,7 @@ typedef struct fgvc_tile_group {
   int32_t n_jobs;
   int32_t u_begin;
   int32_t u_end;
-  int32_t reserved;
+  int32_t out_group; /* which of the job's output lists this group writes (x split + part, see fgvc_affinity_topk_packed) */
 } fgvc_tile_group;
 
 /* fgvc_gather_labels flags */
@@ -155,31 +150,23 @@ FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int3
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
 
-/* Same with a caller-owned workspace, which FGVC_ENGINE_PREFILTER needs (candidate lists + the queue of
- * queries for the exact scan).  `unit_rows` != 0 asserts that every bank slot used was written by K0 with
- * normalize = 1 (the prefilter's error bound needs unit vectors; it refuses otherwise).  Every other engine
- * value behaves exactly like fgvc_affinity_topk and ignores the workspace.
- * fgvc_affinity_topk_workspace_bytes gives the size. */
-FGVC_API int64_t fgvc_affinity_topk_workspace_bytes(int32_t n_jobs, int32_t groups, int32_t n_query, int32_t K);
-FGVC_API int fgvc_prefilter_supported(int32_t bank_format, int32_t H, int32_t W, int32_t C, int32_t K, int32_t groups);
-FGVC_API int fgvc_affinity_topk_ws(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,
-                       int32_t C, const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
-                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
-                       float* topk_val, int32_t* topk_idx, int32_t engine, int32_t unit_rows,
-                       void* workspace, int64_t workspace_bytes, void* stream);
-
 /* K1 on job-packed tiles (F16 bank, tcgen05 fp16 three-term engine only; local_attention.py:318-356 for several
  * consecutive frames of the loop vanilla_tracker.py:345-366 at once): same output as fgvc_affinity_topk
- * for the jobs named by the tile groups (lists are written at [job][group][Nq][K] by job index).  jobs_per_tile in
- * {1, 2, 4}: 128 tile rows = jobs_per_tile jobs x 128 / jobs_per_tile pixels (16x8 | 8x8 | 8x4 block).
- * fgvc_packed_tile_shape reports the pixel block and key-box height the launcher will use (for costing). */
+ * for the jobs named by the tile groups (lists are written at [job][list][Nq][K] by job index, `groups` lists per
+ * job).  A tile group covers the memory entries [u_begin, u_end) of the union tables, cut into `split` contiguous
+ * parts (one CTA or CTA pair each); part y writes list  out_group * split + y  of its jobs, so `groups` must be
+ * split x (number of distinct out_group values) and every (job, list) must be written by exactly one tile group.
+ * jobs_per_tile in {1, 2, 4}: tile rows = jobs_per_tile jobs x a pixel block.  On large maps a tile is a CTA PAIR
+ * (256 rows, tcgen05 cta_group::2: both SMs of the pair multiply the same key box and each stages half of it).
+ * fgvc_packed_tile_shape reports the pixel block of one job, the key-box height and the CTAs per tile the launcher
+ * will use (for costing). */
 FGVC_API int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                        const fgvc_job* jobs, const fgvc_tile_group* tile_groups, int32_t n_tile_groups,
                        const int32_t* union_feat_slot, const int32_t* union_pos, int32_t jobs_per_tile,
-                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
+                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups, int32_t split,
                        float* topk_val, int32_t* topk_idx, void* stream);
 FGVC_API int fgvc_packed_tile_shape(int32_t H, int32_t W, int32_t radius, int32_t mask_mode, int32_t jobs_per_tile,
-                       int32_t* tile_h, int32_t* tile_w, int32_t* box_h);
+                       int32_t* tile_h, int32_t* tile_w, int32_t* box_h, int32_t* ctas_per_tile);
 
 /* test hook (tcgen05 engine, groups = 1, use with ONE query tile): additionally dumps the
  * raw 128 x 128 accumulator tile of the first dbg_max_boxes key boxes to

@@ -21,28 +21,30 @@ TIGHT = 2e-5        # what we actually expect away from ties
 GAP_EPS = 3e-5      # affinity/temperature units: cos gap 2e-6 at temperature 0.07
 
 
-# engine name -> (engine id, feature-bank split): CUDA-core fp32, tcgen05 3xTF32, tcgen05 fp16 three-term,
-# tcgen05 fp16 prefilter + exact rescoring (the default for F16 banks of unit rows)
-ENGINES = ["simt", "tc", "tc16", "tcp"]
+# engine name -> (engine id, feature-bank split): CUDA-core fp32, tcgen05 3xTF32, tcgen05 fp16 three-term on
+# single-CTA tiles (tc16) and on CTA-pair tiles (tc16x2: cta_group::2, 256 rows per key box)
+ENGINES = ["simt", "tc", "tc16", "tc16x2"]
 
 
 def _eng(name):
+    """kwargs of the operators for an engine; the tile form of the fp16 tensor engine is forced through the
+    environment (read by the launcher on every call), every other name leaves the launcher's own choice."""
     import fgvc_b200
+    if name in ("tc16", "tc16x2"):
+        os.environ["FGVC_TC16_PAIR"] = "1" if name == "tc16x2" else "0"
+    else:
+        os.environ.pop("FGVC_TC16_PAIR", None)
     return {"simt": dict(engine_id=fgvc_b200.ENGINE_SIMT, split="tf32"),
             "simt16": dict(engine_id=fgvc_b200.ENGINE_SIMT, split="f16"),
             "tc": dict(engine_id=fgvc_b200.ENGINE_TCGEN05, split="tf32"),
             "tc16": dict(engine_id=fgvc_b200.ENGINE_TCGEN05, split="f16"),
-            "tcp": dict(engine_id=fgvc_b200.ENGINE_PREFILTER, split="f16"),
+            "tc16x2": dict(engine_id=fgvc_b200.ENGINE_TCGEN05, split="f16"),
             "auto": dict(engine_id=fgvc_b200.ENGINE_AUTO)}[name]
 
 
 def _skip_if_tc_unsupported(name, C, H=64, W=64, K=10):
     from fgvc_b200 import _lib
-    if name == "tcp":
-        if not _lib.load().fgvc_prefilter_supported(_lib.BANK_F16, H, W, C, K, 1):
-            pytest.skip("prefilter engine does not take this shape (C % 64 == 0, C <= 256)")
-        return
-    fmt = {"tc": _lib.BANK_TF32, "tc16": _lib.BANK_F16}.get(name)
+    fmt = {"tc": _lib.BANK_TF32, "tc16": _lib.BANK_F16, "tc16x2": _lib.BANK_F16}.get(name)
     if fmt is not None and not _lib.load().fgvc_tc_supported(fmt, H, W, C, K):
         pytest.skip("tcgen05 engine does not take this shape (3xTF32: C % 32 == 0; fp16 split: C % 64 == 0, C <= 256)")
 
@@ -221,8 +223,7 @@ def test_groups_do_not_change_results():
     q, k = f[5][None], f[:5].permute(1, 0, 2, 3)[None].contiguous()
     v = torch.rand(1, 5, 5, 24, 28, generator=g).cuda()
     import fgvc_b200
-    for eng, split in ((fgvc_b200.ENGINE_SIMT, "tf32"), (fgvc_b200.ENGINE_TCGEN05, "f16"),
-                       (fgvc_b200.ENGINE_PREFILTER, "f16")):
+    for eng, split in ((fgvc_b200.ENGINE_SIMT, "tf32"), (fgvc_b200.ENGINE_TCGEN05, "f16")):
         base = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, eng, groups=1, split=split)
         for gr in (2, 3, 5):
             out = ops._propagate(q, k, v, 5, "circle", 0.07, 10, True, 0, eng, groups=gr, split=split)
@@ -239,61 +240,9 @@ def test_engines_agree_on_clear_queries():
     ex = O.propagate_exact(q, k, v, radius=6, temperature=0.07, topk=10)
     clear = (ex["gap"] > GAP_EPS).view(1, 1, 30, 40).cuda()
     outs = [fgvc_b200.masked_attention_efficient_v2(q.cuda(), k.cuda(), v.cuda(), 6, temperature=0.07, topk=10,
-                                                    **_eng(name)) for name in ("simt", "simt16", "tc", "tc16", "tcp")]
+                                                    **_eng(name)) for name in ("simt", "simt16", "tc", "tc16", "tc16x2")]
     for o in outs[1:]:
         assert float(((outs[0] - o).abs() * clear).max()) < TIGHT
-
-
-def _prefilter_queue_len(n_jobs, groups, n_pix, K):
-    """number of queries the last prefilter launch on this stream queued for the exact scan (stage C)"""
-    from fgvc_b200 import engine
-    kp = 4 if K <= 2 else (10 if K <= 10 else 16)
-    ws = engine._WORKSPACES[(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)]
-    off = n_jobs * groups * n_pix * 4 * kp * 8
-    return int(ws[off:off + 4].view(torch.int32).item())
-
-
-def test_prefilter_overflow_takes_the_exact_scan():
-    """Blocks of 4x4 pixels share one feature vector in every frame: every query has 48 exactly tied best
-    candidates, every partial list is full inside the 2-eps band, so EVERY query must be re-done by the exact
-    scan (stage C of topk_tc16p.cu).  Labels are block-constant too, so the tied choice does not matter."""
-    import fgvc_b200
-    from fgvc_b200 import ops
-    g = torch.Generator().manual_seed(77)
-    H, W, C, T, L = 24, 32, 64, 3, 5
-    low = torch.randn(C, H // 4, W // 4, generator=g).relu() + 0.01
-    f = low.repeat_interleave(4, 1).repeat_interleave(4, 2)
-    q, k = f[None], f[None, :, None].repeat(1, 1, T, 1, 1).contiguous()
-    lab = torch.rand(L, H // 4, W // 4, generator=g).repeat_interleave(4, 1).repeat_interleave(4, 2)
-    v = lab[None, :, None].repeat(1, 1, T, 1, 1).contiguous()
-    got = ops._propagate(q.cuda(), k.cuda(), v.cuda(), 6, "circle", 0.07, 10, True, 0, fgvc_b200.ENGINE_PREFILTER,
-                         groups=1, split="f16")
-    torch.cuda.synchronize()
-    assert _prefilter_queue_len(1, 1, H * W, 10) == H * W
-    want = _port64(q, k, v, radius=6, temperature=0.07, topk=10)
-    assert (got.cpu() - want).abs().max() < 1e-5
-    # and a tie-free input queues (almost) nothing
-    f2 = _coherent(g, T + 1, C, H, W)
-    q2, k2 = f2[T][None], f2[:T].permute(1, 0, 2, 3)[None].contiguous()
-    ops._propagate(q2.cuda(), k2.cuda(), v.cuda(), 6, "circle", 0.07, 10, True, 0, fgvc_b200.ENGINE_PREFILTER,
-                   groups=1, split="f16")
-    torch.cuda.synchronize()
-    assert _prefilter_queue_len(1, 1, H * W, 10) <= 0.02 * H * W
-
-
-def test_prefilter_needs_unit_rows():
-    """un-normalised features have no error bound for the fp16 prefilter: loud, and AUTO uses the exact engine"""
-    import fgvc_b200
-    g = torch.Generator().manual_seed(78)
-    f = _coherent(g, 3, 64, 16, 16).cuda()
-    q, k = f[2][None], f[:2].permute(1, 0, 2, 3)[None].contiguous()
-    v = torch.rand(1, 4, 2, 16, 16, generator=g).cuda()
-    with pytest.raises(fgvc_b200.FgvcError):
-        fgvc_b200.masked_attention_efficient_v2(q, k, v, 4, temperature=0.07, topk=5, normalize=False,
-                                                engine_id=fgvc_b200.ENGINE_PREFILTER, split="f16")
-    got = fgvc_b200.masked_attention_efficient_v2(q, k, v, 4, temperature=0.07, topk=5, normalize=False)
-    want = O.propagate_port(q.cpu(), k.cpu(), v.cpu(), radius=4, temperature=0.07, topk=5, normalize=False)
-    assert (got.cpu() - want).abs().max() < 1e-3
 
 
 # ---------------------------------------------------------- size-independent properties
@@ -623,11 +572,13 @@ def test_clip_host_pipeline_equals_resident_run():
     assert float((err > TOL).float().mean()) <= 2e-3
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("geom", [(26, 37, 64, 10, 14, 6), (24, 40, 256, 12, 9, 3)])
-def test_job_packed_tiles_equal_unpacked(monkeypatch, geom):
-    """csrc/topk_tc16g.cu: J = 2 / 4 consecutive query frames per M = 128 tile must give the same top-k lists as
-    one job per tile -- values bit for bit (same MMA sequence per (query, key) pair), indices up to the order of
-    exactly tied values (frame 0 twice in the memory)."""
+def test_job_packed_tiles_equal_unpacked(monkeypatch, geom, pair):
+    """csrc/topk_tc16.cu: J = 2 / 4 consecutive query frames per tile (single-CTA tiles and CTA pairs) must give the
+    same top-k lists as one job per tile -- values bit for bit (same MMA sequence per (query, key) pair), indices up
+    to the order of exactly tied values (frame 0 twice in the memory).  The aligned packings ("2a", "4a": memory
+    frames in J classes, one partial list per class) must give the same propagated labels."""
     from fgvc_b200 import engine, _lib
     H, W, C, T, precede, r = geom
     g = torch.Generator().manual_seed(H)
@@ -641,24 +592,30 @@ def test_job_packed_tiles_equal_unpacked(monkeypatch, geom):
     labels = engine.LabelBank(T, 5, H, W, torch.device("cuda"))
     first = torch.rand(5, H, W, generator=g).cuda()
     out, prop = {}, {}
-    for J in (1, 2, 4):
-        monkeypatch.setenv("FGVC_PACK", str(J))
-        lists = engine.affinity_topk(bank, tb, r, 10, groups=1, engine=_lib.ENGINE_TCGEN05)
-        torch.cuda.synchronize()
-        out[J] = (lists.val.clone(), lists.idx.clone())
-        # with the memory split into groups the per-group lists differ by construction (the UNION list is what is
-        # split); what must agree is the merged result, i.e. the propagated labels
-        lists2 = engine.affinity_topk(bank, tb, r, 10, groups=3, engine=_lib.ENGINE_TCGEN05)
+    monkeypatch.setenv("FGVC_TC16_PAIR", str(pair))
+    for J in ("1", "2", "4", "2a", "4a"):
+        monkeypatch.setenv("FGVC_PACK", J)
+        if not J.endswith("a"):
+            lists = engine.affinity_topk(bank, tb, r, 10, groups=1, engine=_lib.ENGINE_TCGEN05)
+            torch.cuda.synchronize()
+            out[J] = (lists.val.clone(), lists.idx.clone())
+            # with the memory split into groups the per-group lists differ by construction (the UNION list is what
+            # is split); what must agree is the merged result, i.e. the propagated labels
+            lists2 = engine.affinity_topk(bank, tb, r, 10, groups=3, engine=_lib.ENGINE_TCGEN05)
+        else:
+            lists2 = engine.affinity_topk(bank, tb, r, 10, engine=_lib.ENGINE_TCGEN05)
+            assert lists2.groups % int(J[0]) == 0
         labels.put_nchw(first, 0)
         for j in range(len(tb)):
             engine.gather_labels(lists2, tb, j, j + 1, labels, 0.07)
         prop[J] = labels.buf.clone()
     monkeypatch.delenv("FGVC_PACK", raising=False)
-    for J in (2, 4):
-        assert torch.equal(out[J][0], out[1][0]), J
-        same = out[J][1] == out[1][1]
+    monkeypatch.delenv("FGVC_TC16_PAIR", raising=False)
+    for J in ("2", "4"):
+        assert torch.equal(out[J][0], out["1"][0]), J
+        same = out[J][1] == out["1"][1]
         # where indices differ the values must be exactly tied with a neighbour in the list
-        v = out[1][0]
+        v = out["1"][0]
         tied = torch.zeros_like(same)
         tied[..., 1:] |= v[..., 1:] == v[..., :-1]
         tied[..., :-1] |= v[..., :-1] == v[..., 1:]
@@ -672,10 +629,11 @@ def test_job_packed_tiles_equal_unpacked(monkeypatch, geom):
                 mem = torch.tensor(tb.mem_feat[tb.jobs[j][1]:tb.jobs[j][2]], device=idx.device) & ~_lib.MEM_UNMASKED
                 slot[j] = mem[pos[j].clamp_max(mem.numel() - 1).long()].to(idx.dtype)
             return slot * n_pix + pix
-        same_key = keys(out[J][1]) == keys(out[1][1])
+        same_key = keys(out[J][1]) == keys(out["1"][1])
         assert bool((same | tied | same_key).all()), J
         assert float(same.float().mean()) > 0.95          # the rest: swapped exact ties of the doubled frame 0
-        assert (prop[J] - prop[1]).abs().max() < 1e-6, J
+    for J in ("2", "4", "2a", "4a"):
+        assert (prop[J] - prop["1"]).abs().max() < 1e-6, J
 
 
 def test_gather_chain_equals_per_frame_launches(monkeypatch):

@@ -38,7 +38,7 @@ def test_job_table_layout():
 
 
 def test_job_packing_tables_reproduce_every_memory_list():
-    """JobTable.packed (host side of csrc/topk_tc16g.cu): the union list of a tile group, read through union_pos,
+    """JobTable.packed (host side of csrc/topk_tc16.cu): the union list of a tile group, read through union_pos,
     must give back every job's own memory multiset in its own order -- incl. frame 0 twice while t <= precede."""
     for precede, T, unmasked in ((3, 9, 0), (20, 30, 1), (5, 7, 0)):
         tb = engine.JobTable()
@@ -66,7 +66,38 @@ def test_job_packing_tables_reproduce_every_memory_list():
                     assert (upos[u0:u1, li] == -1).all()
             assert seen_jobs == list(range(len(tb)))
             assert tb.union_sizes(0, len(tb), J) == [g[6] - g[5] for g in tg.tolist()]
-    # long memories pack, short ones do not (cost model over the exact box counts needs the library: skipped here)
+
+
+def test_aligned_packing_covers_every_entry_once_and_wastes_nothing():
+    """JobTable.packed(aligned=True): memory frames in J classes (slot % J), query frames of class a grouped with phase
+    a.  Every memory entry of every job appears in exactly one class, every job has a tile group in EVERY class
+    (possibly with no entry: its list must still be written), and in the steady state of a sliding window every
+    job of a group uses every union entry (no wasted tile rows)."""
+    precede, T, J = 20, 64, 4
+    tb = engine.JobTable()
+    for t in range(1, T):
+        mem = engine.memory_frames(t, precede, True)
+        tb.add(t, mem, mem, t)
+    tg, uent, upos = tb.packed(0, len(tb), J, "cpu", aligned=True)
+    covered = {j: [] for j in range(len(tb))}
+    classes = {j: set() for j in range(len(tb))}
+    for g in tg.tolist():
+        members, n, u0, u1, cls = g[:4], g[4], g[5], g[6], g[7]
+        assert 0 <= cls < J and 1 <= n <= J
+        for u in range(u0, u1):
+            assert (int(uent[u]) & ~0x40000000) % J == cls
+        for li in range(n):
+            classes[members[li]].add(cls)
+            covered[members[li]] += [int(upos[u, li]) for u in range(u0, u1) if int(upos[u, li]) >= 0]
+        # steady state (window full, first frame outside the window): no wasted rows
+        if n == J and all(tb.jobs[m][0] > precede + J for m in members[:n]):
+            assert (upos[u0:u1, :n] >= 0).all()
+    for j in range(len(tb)):
+        assert classes[j] == set(range(J))
+        assert sorted(covered[j]) == list(range(tb.jobs[j][2] - tb.jobs[j][1]))
+    plain = sum(tb.union_sizes(0, len(tb), J))
+    aligned = sum(tb.union_sizes(0, len(tb), J, aligned=True))
+    assert aligned < 0.93 * plain
 
 
 def test_pick_packing_follows_the_memory_length():
@@ -79,16 +110,16 @@ def test_pick_packing_follows_the_memory_length():
             tb.add(t, mem, mem, t)
         return tb
     long_mem, short_mem = table(64, 20), table(50, 5)
-    assert engine.pick_packing(long_mem, 0, len(long_mem), 60, 107, 12, 0) in (2, 4)
-    assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0) == 1
-    assert engine.pick_packing(long_mem, 3, 4, 60, 107, 12, 0) == 1            # a single job has nothing to share
+    assert engine.pick_packing(long_mem, 0, len(long_mem), 60, 107, 12, 0)[0] in (2, 4)
+    assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0)[0] in (1, 2)
+    assert engine.pick_packing(long_mem, 3, 4, 60, 107, 12, 0) == (1, False)   # a single job has nothing to share
     # exact accounting used by bench.py: packing must reduce the dense pairs of the long-memory clip
     d1 = engine.dense_pairs(long_mem, 0, len(long_mem), 60, 107, 12, 0, 1)
     d4 = engine.dense_pairs(long_mem, 0, len(long_mem), 60, 107, 12, 0, 4)
-    assert 0.7 * d1 < d4 < 0.9 * d1
+    assert 0.6 * d1 < d4 < 0.9 * d1
     os.environ["FGVC_PACK"] = "2"
     try:
-        assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0) == 2
+        assert engine.pick_packing(short_mem, 0, len(short_mem), 128, 128, 15, 0) == (2, False)
     finally:
         del os.environ["FGVC_PACK"]
 

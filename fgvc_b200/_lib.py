@@ -73,9 +73,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if not _build.up_to_date():
+        # torchrun starts every rank at once: one builds (exclusive file lock, the .so is replaced atomically),
+        # the others wait for the lock and find the library current
+        import fcntl
+        with open(os.path.join(HERE, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                _build.build()
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol

@@ -202,25 +202,79 @@ def collect_results_cpu(result_part, size, tmpdir=None):
     return _interleave([pickle.loads(b) for b in gathered], size)
 
 
-# ------------------------------------------------------------------ single long video: shard the points
+# ------------------------------------------------------------------ single long video: two-phase sharding
+# the affinity / top-k lists depend only on features (phase 1: tensor-bound, parallel over frames),
+# the recurrence lives only in the label gather (phase 2: sequential in time, parallel over label channels).  So one
+# long video scales its COMPUTE across ranks by sharding phase 1 over frame ranges, exchanging the sparse lists once
+# (8 * k * Nq bytes per frame), and sharding phase 2 over the tracked points; results are identical to one GPU.
 def point_shard(n_points, rank, world):
-    """Contiguous slice of the tracked points owned by ``rank`` (label channels
-    never mix, so a long video shards by point with no per-frame exchange)."""
+    """Contiguous slice of the tracked points owned by ``rank`` (label channels never mix)."""
     lo = (n_points * rank) // world
     hi = (n_points * (rank + 1)) // world
     return lo, hi
 
 
+def frame_shard(n_jobs, rank, world):
+    """(lo, hi, per): jobs [lo, hi) of phase 1 owned by ``rank``; every rank owns a slot of ``per`` jobs in the
+    gathered list buffer (the last ranks' slots may be partly or wholly padding)."""
+    per = -(-n_jobs // world) if n_jobs else 0
+    lo, hi = min(n_jobs, rank * per), min(n_jobs, (rank + 1) * per)
+    return lo, hi, per
+
+
+def gather_job_lists(buf, per, rank, world):
+    """``buf`` [per * world, ...]: every rank filled its own slot [rank*per, (rank+1)*per); afterwards every rank
+    holds all slots.  One all_gather (in place over NCCL: the send buffer is the rank's slot of the receive buffer)."""
+    if world == 1 or per == 0:
+        return buf
+    assert buf.shape[0] == per * world and buf.is_contiguous()
+    mine = buf[rank * per:(rank + 1) * per]
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(buf, mine)
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.clone())
+        for r, p in enumerate(parts):
+            buf[r * per:(r + 1) * per].copy_(p)
+    return buf
+
+
+def gather_point_tracks(local, group_sizes, rank, world):
+    """Phase-2 result exchange.  ``local`` [T, sum_g pad_g, 2]: for every group g the tracks of this rank's point
+    slice (point_shard of the group's size), left-aligned in a slot of pad_g = ceil(P_g / world) columns.  One
+    all_gather; returns the per-group [T, P_g, 2] tracks in the original point order on every rank."""
+    pads = [-(-n // world) for n in group_sizes]
+    assert local.shape[1] == sum(pads)
+    if world == 1:
+        parts = [local]
+    else:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local.contiguous())
+    out, off = [], 0
+    for n, pad in zip(group_sizes, pads):
+        cols = []
+        for r in range(world):
+            lo, hi = point_shard(n, r, world)
+            cols.append(parts[r][:, off:off + (hi - lo)])
+        out.append(torch.cat(cols, dim=1) if cols else local[:, :0])
+        off += pad
+    return out
+
+
 def sharded_forward_test(model, rgbs, query_points, trajectories, visibilities, **kw):
-    """``forward_test`` of one (long) video with the tracked points sharded across the ranks of the
-    default process group.  Every rank encodes the clip and recomputes the (label-independent)
-    affinity top-k; it propagates only its slice of the points.  The only collective is one
-    ``all_gather`` of the ``[T, P_rank, 2]`` tracks.  Returns the reference's 5-tuple
-    (vanilla_tracker.py:227-303) on every rank, identical to the un-sharded call."""
+    """``forward_test`` of one (long) video over the ranks of the default process group; returns the reference's
+    5-tuple (vanilla_tracker.py:227-303) on every rank, identical to the un-sharded call.
+    A tracker that implements the two-phase split (``VanillaTracker``: ``forward_test(..., shard=(rank, world))``)
+    shards the K1 launch over frame ranges, all-gathers the top-k lists, and propagates only its slice of the
+    points; collectives: one all_gather of the lists, one of the ``[T, P_rank, 2]`` tracks.
+    Any other model falls back to sharding the points only (every rank then repeats the label-independent work)."""
     rank, world = get_dist_info()
     if world == 1:
         return model(test_mode=True, rgbs=rgbs, query_points=query_points, trajectories=trajectories,
                      visibilities=visibilities, **kw)
+    if getattr(model, "two_phase_sharding", False):
+        return model(test_mode=True, rgbs=rgbs, query_points=query_points, trajectories=trajectories,
+                     visibilities=visibilities, shard=(rank, world), **kw)
     assert rgbs.shape[0] == 1
     B, T = rgbs.shape[:2]
     P = query_points.shape[1]

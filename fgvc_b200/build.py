@@ -32,10 +32,18 @@ def _digest():
     for p in sorted(os.listdir(CSRC)) + [inc]:
         path = p if os.path.isabs(p) else os.path.join(CSRC, p)
         with open(path, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())      # (not the path: the tree moves between boxes)
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def up_to_date():
+    """the library exists and was built from the current sources (digest stamp)"""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read() == _digest()
+    except OSError:
+        return False
 
 
 def build(force=False, verbose=False):
@@ -59,11 +67,13 @@ def build(force=False, verbose=False):
         if verbose or "warning" in out:
             print(out, file=sys.stderr)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+    tmp_lib = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp_lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
            "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB)            # atomic: a concurrent loader sees the old or the new file, never half of one
     with open(STAMP, "w") as f:
         f.write(dig)
     return LIB

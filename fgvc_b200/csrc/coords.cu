@@ -490,11 +490,9 @@ extern "C" int fgvc_heatmap_coords(const float* maps, int32_t n_maps, int32_t H,
   FGVC_CHECK_ARG(topk >= 1 && topk <= CK, "fgvc_heatmap_coords: topk=%d not in [1,%d]", topk, CK);
   size_t smem = (size_t)H * W * sizeof(float);
   int use_smem = smem <= 160 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per launch: the attribute is per device, and a process may use several
+  if (use_smem && smem > 48 * 1024)
     FGVC_CUDA(cudaFuncSetAttribute(heatmap_coords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
   heatmap_coords_kernel<<<n_maps, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(maps, H, W, out_h, out_w,
                                                                                      topk, use_smem, out_xy);
   FGVC_LAUNCH_CHECK();

@@ -256,13 +256,17 @@ static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int grou
                                                temperature, flags, cw, crow);
   FGVC_LAUNCH_CHECK();
   // all CTAs must be co-resident (they spin on the grid barrier): cooperative launch, sized from the occupancy
-  static int max_ctas = 0;
+  // (per device of the calling thread; cached per device index, written once with the same value by any thread)
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  FGVC_CUDA(cudaGetDevice(&dev));
+  int max_ctas = (dev >= 0 && dev < 64) ? cached[dev].load(std::memory_order_relaxed) : 0;
   if (max_ctas == 0) {
-    int dev = 0, sms = 0, occ = 0;
-    FGVC_CUDA(cudaGetDevice(&dev));
+    int sms = 0, occ = 0;
     FGVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FGVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_chain_kernel<K>, 256, 0));
     max_ctas = sms * (occ < 1 ? 1 : occ);
+    if (dev >= 0 && dev < 64) cached[dev].store(max_ctas, std::memory_order_relaxed);
   }
   const int l4n = Lp / 4;
   // latency-bound (a few microseconds per frame): as many CTAs as can be co-resident, so that a CTA's slice is

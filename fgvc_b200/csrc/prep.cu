@@ -206,11 +206,11 @@ extern "C" int fgvc_prep_features(const float* src, int64_t src_frame_stride, in
   int n_pix = H * W;
   size_t smem = (size_t)(C * 33 + 32) * sizeof(float);
   FGVC_CHECK_ARG(bank_format == FGVC_BANK_TF32 || bank_format == FGVC_BANK_F16, "fgvc_prep_features: bad bank format");
-  static bool attr_set = false;
-  if (!attr_set) {
-    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+  if (smem > 48 * 1024) {      // per launch: the attribute is per device, and a process may use several
+    if (bank_format == FGVC_BANK_TF32)
+      FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    else
+      FGVC_CUDA(cudaFuncSetAttribute(prep_features_kernel<FGVC_BANK_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   dim3 grid(cdiv(n_pix, 32), n_frames);
   if (bank_format == FGVC_BANK_TF32)

@@ -30,32 +30,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ uint64_t global_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// bounded wait: a protocol bug traps (launch error) after 2 s of wall clock instead of hanging the GPU.  The retry
-// loop is kept tiny (spinning warps share issue slots with the MMA / TMA warps of the same scheduler).
+// Waits are hardware-suspended: mbarrier.try_wait with a time hint parks the thread until the phase flips (it also
+// wakes, spuriously, on other barrier traffic of the CTA), so the retry loop must stay tiny -- it shares the ALU pipe
+// with the warps that have work (profiles/r2_b_epilogue.md: a loop that also read the global timer was 30 % of all
+// instructions of K1).  A protocol bug still ends in a trap (launch error) instead of a hang: the retry counter is
+// bounded (each retry lasts between a few hundred ns and the 10 ms hint).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 63u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
-  }
+#pragma unroll 1
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();
 }
-// same for the epilogue warps, which wait about a box time (~1 us) per hand-off: sleep between
-// probes so that 16 waiting warps do not take issue slots from the warps that have work
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
-  uint32_t spins = 0;
-  do {
-    __nanosleep(256);
-    if ((++spins & 63u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
-  } while (!mbar_try_wait(bar, parity));
-}
+// (kept as a separate name for the epilogue's accumulator waits)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(

@@ -27,6 +27,8 @@
 // above the thread's running K-th value are inserted into a sorted register list in warp-wide rounds.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace fgvc {
@@ -36,10 +38,12 @@ constexpr int RING_BYTES = 192 * 1024;
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_NC = 64;                     // keys of a box staged per CTA (x NCTA = N of the MMA)
 constexpr int AHI_COL = 256, ALO_COL = 384;
-constexpr int EPI_WG = 4;
+constexpr int MAX_ACC = 4;                     // accumulator tiles in TMEM columns [0, 256): 256 / N of them, at most 4
+constexpr int EPI_WG = 4;                     // epilogue warpgroups: 4 warps per TMEM lane quarter share the rows of a box
 constexpr int THREADS = 64 + 128 * EPI_WG;
-constexpr int MAX_BOXES = 4096;                // per box list (masked halo / whole frame)
-constexpr int AUX_BYTES = 1024 + 2 * MAX_BOXES * 4;
+constexpr int MAX_BOXES = 3840;                // per box list (masked halo / whole frame)
+constexpr int THR_BYTES = 128 * EPI_WG * 4;    // running K-th values of the partial lists, shared per query
+constexpr int AUX_BYTES = 1024 + THR_BYTES + 2 * MAX_BOXES * 4;
 constexpr int SMEM_BYTES = RING_BYTES + AUX_BYTES;
 constexpr int TW_MAX_MEM = 64;                 // window mode: memory entries per call
 
@@ -48,7 +52,8 @@ struct Params {
   int radius, mode, reach;
   int QH, QW, qw_shift;        // pixel block of ONE job inside a tile
   int lpj_shift;               // log2(tile rows per job): rows = J jobs x (128 * NCTA / J) pixels
-  int BH;                      // key-box height: a box = 16 x BH pixels = N keys, BH / NCTA rows staged per CTA
+  int BH, bh_shift;            // key-box height (a power of two): a box = 16 x BH pixels = N keys, BH / NCTA rows
+                               // staged per CTA
   int tiles_x;
   int lists_per_job, split, k_out;   // output lists per job; a tile group's memory list is split `split` ways (grid.y)
   const fgvc_job* jobs;
@@ -124,8 +129,10 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// (default semantics, as CUTLASS's umma_arrive_2x1SM_sm0: the .release.cluster form costs a MEMBAR.ALL.GPU per arrival,
+// and what it would order -- the tcgen05.ld results -- is already complete: tcgen05.wait::ld + fence::before_thread_sync)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -147,6 +154,54 @@ __device__ __forceinline__ void tma_box(const CUtensorMap* map, uint32_t leader_
         : "memory");
 }
 
+// One key row of a box for one warp: r[j] = accumulator (256 x affinity) of this lane's query against key j of the row,
+// `bits` = the lane's in-mask keys.  Most rows hold nothing above the running K-th values once the lists are warm:
+// a 3-input max tree over the row (8 instructions) and one vote reject those.  Otherwise candidates (in-mask and above
+// the lane's K-th value) are inserted into the sorted register list in warp-wide rounds: in every round each lane that
+// still has a candidate takes its next one, so a round serves several lanes at once.
+// experiment counters (build with -DFGVC_TC16_STATS, run with FGVC_TC16_EXP & 16): row scans, rows past the quick reject, insertion rounds, list insertions
+__device__ unsigned long long g_stats[8];
+
+template <int K>
+__device__ __forceinline__ void scan_row(const uint32_t (&r)[16], uint32_t bits, TopK<K>& top, int kbase, float floor_,
+                                         int stats) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  const float thr = fmaxf(top.thr(), floor_);
+  float mx = fmaxf(fmaxf(v[0], v[1]), v[2]);
+#pragma unroll
+  for (int j = 3; j < 15; j += 2) mx = fmaxf(fmaxf(mx, v[j]), v[j + 1]);
+  mx = fmaxf(mx, v[15]);
+#ifdef FGVC_TC16_STATS
+  if (stats && (threadIdx.x & 31) == 0) atomicAdd(&g_stats[0], 1ull);
+#endif
+  if (!__any_sync(0xffffffffu, bits != 0 && mx > thr)) return;
+#ifdef FGVC_TC16_STATS
+  if (stats && (threadIdx.x & 31) == 0) atomicAdd(&g_stats[1], 1ull);
+#endif
+  uint32_t cand = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cand |= (v[j] > thr) ? (1u << j) : 0u;
+  cand &= bits;
+  while (__any_sync(0xffffffffu, cand != 0)) {
+#ifdef FGVC_TC16_STATS
+    if (stats && (threadIdx.x & 31) == 0) atomicAdd(&g_stats[2], 1ull);
+#endif
+    if (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float x = select16(v, j);
+      if (x > fmaxf(top.thr(), floor_)) {
+        top.push(x, kbase + j);
+#ifdef FGVC_TC16_STATS
+        if (stats) atomicAdd(&g_stats[3], 1ull);
+#endif
+      }
+    }
+  }
+}
+
 template <int K, int NCTA, bool WIN>
 __global__ void __launch_bounds__(THREADS, 1)
 affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __half* __restrict__ bank, const Params p) {
@@ -154,17 +209,18 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
   uint8_t* ring = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + RING_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* a_bar = tempty_bar + 2;               // query operand written to TMEM
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [MAX_ACC]
+  uint64_t* tempty_bar = tfull_bar + MAX_ACC;     // [MAX_ACC]
+  uint64_t* a_bar = tempty_bar + MAX_ACC;         // query operand written to TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
   int* nbox = reinterpret_cast<int*>(tmem_slot + 2);      // [2] number of boxes in each list
-  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);     // [reach+1] <= 128 entries (window mode: rect[4])
+  int* halfw = reinterpret_cast<int*>(tmem_slot + 4);     // [reach + 2] <= 130 entries, then rect[4] (window mode)
   // box lists (by | bx << 16): [0] = radius halo of this query tile minus boxes no query can see,
   // [1] = every box of the frame (unmasked memory entries).  Identical for all memory entries, so
   // the three warp roles just walk a list instead of re-deriving the geometry per box.
   // Window mode: ONE list (this CTA's chunk of its entry's rectangle) over both areas.
-  uint32_t* boxes = reinterpret_cast<uint32_t*>(ring + RING_BYTES + 1024);
+  float* thr_sh = reinterpret_cast<float*>(ring + RING_BYTES + 1024);      // [128 queries][EPI_WG lists]
+  uint32_t* boxes = reinterpret_cast<uint32_t*>(ring + RING_BYTES + 1024 + THR_BYTES);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,6 +271,10 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
 
   const int NC = 16 * p.BH / NCTA;             // keys of a box staged by this CTA
   const int N = 16 * p.BH;                     // keys of a box = accumulator columns
+  // The MMA warp may run n_acc - 1 boxes ahead of the epilogue's loads: the scan time of a box varies a lot (list
+  // insertions), and with only two tiles both sides kept waiting for each other (profiles/r2_b_epilogue.md)
+  const int n_acc = min(MAX_ACC, 256 / N);
+  const uint32_t acc_cols = 256u / (uint32_t)n_acc;
   const int n_kc = p.C / 64;
   // one stage = this CTA's part of one whole key box (all C channels: n_kc chunks of [hi rows ; lo rows] x 128 B),
   // so the single issuing threads pay one barrier round trip per box instead of one per 64 channels
@@ -226,7 +286,7 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     for (int s = 0; s < n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * EPI_WG * NCTA); }
+    for (int b = 0; b < MAX_ACC; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 4 * EPI_WG * NCTA); }
     mbar_init(a_bar, 4 * EPI_WG * NCTA);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -240,16 +300,23 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
   }
-  if constexpr (!WIN) {
-    for (int d = threadIdx.x; d <= p.reach; d += THREADS) {
+  // half width of the mask at row distance d (d = 0 .. reach), -1 beyond (one sentinel entry)
+  if constexpr (WIN) {
+    for (int d = threadIdx.x; d <= p.rf + 1; d += THREADS) halfw[d] = d <= p.rf ? p.rf : -1;
+  } else {
+    for (int d = threadIdx.x; d <= p.reach + 1; d += THREADS) {
       int hw = -1;
-      if (p.mode == FGVC_MASK_CIRCLE) {
-        while (hw + 1 <= p.reach && (hw + 1) * (hw + 1) + d * d < p.radius * p.radius) ++hw;
-      } else {
-        hw = p.radius;
+      if (d <= p.reach) {
+        if (p.mode == FGVC_MASK_CIRCLE) {
+          while (hw + 1 <= p.reach && (hw + 1) * (hw + 1) + d * d < p.radius * p.radius) ++hw;
+        } else {
+          hw = p.radius;
+        }
       }
       halfw[d] = hw;
     }
+  }
+  if constexpr (!WIN) {
     if (warp == 2 || warp == 3) {          // one warp per list
       const int li = warp - 2;
       const Walk w = make_walk(p, li ? FGVC_MEM_UNMASKED : 0, qy0, qx0);
@@ -297,7 +364,7 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     }
   } else if (warp >= 2 && warp < 6) {
     // ---- window mode: bounding rectangle of the tile's window centres in this CTA's memory entry (lane = query)
-    int* rect = halfw;
+    int* rect = halfw + 132;                                // (the table above holds <= 130 entries)
     const int m = (warp - 2) * 32 + lane;
     const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
     const bool qvalid = qy < p.HQ && qx < p.WQ;
@@ -376,19 +443,19 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
       if (elect_one()) {
         const uint32_t idesc = make_idesc_f16(128 * NCTA, N);
         int stage = 0, buf = 0;
-        uint32_t phase = 0, tphase0 = 0, tphase1 = 0;
+        uint32_t phase = 0, tpar = 0;                  // tpar: bit b = parity of accumulator b's next "drained" phase
         const uint32_t ring_u32 = smem_u32(ring);
         const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
         const uint64_t lo_off = (uint64_t)((NC * 128) >> 4);           // lo rows follow the hi rows of a chunk
         // The barrier probes of box it+1 are issued while the last MMAs of box it are still queued in
         // the tensor pipe, so the pipe does not drain during the ~100-cycle try_wait round trips.
         if (n_total > 0) {
-          mbar_wait(tempty_bar + 0, tphase0 ^ 1);
+          mbar_wait(tempty_bar + 0, 1);
           mbar_wait(full_bar + 0, phase);
           tc_fence_after();
         }
         for (int it = 0; it < n_total; ++it) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+          const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_cols;
           const uint32_t sa = ring_u32 + (uint32_t)(stage * stage_bytes);
           for (int kc = 0; kc < n_kc; ++kc) {
             const uint64_t b = desc_hi | (uint64_t)((sa + (uint32_t)(kc * chunk_bytes)) >> 4);
@@ -404,9 +471,10 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
           }
           const int nstage = (stage + 1 == n_stages) ? 0 : stage + 1;
           const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
-          const int nbuf = buf ^ 1;
+          const int nbuf = (buf + 1 == n_acc) ? 0 : buf + 1;
+          tpar ^= 1u << buf;                              // this tile's next drain completes the following phase
           if (it + 1 < n_total) {
-            mbar_wait(tempty_bar + nbuf, (nbuf ? tphase1 : tphase0) ^ 1);   // epilogue drained the other accumulator
+            mbar_wait(tempty_bar + nbuf, ((tpar >> nbuf) & 1u) ^ 1u);       // epilogue drained the next accumulator
             mbar_wait(full_bar + nstage, nphase);                           // next key box landed
             tc_fence_after();
           }
@@ -420,7 +488,6 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
           }
           umma_commit_all<NCTA>(empty_bar + stage);     // smem stage free (in both CTAs) once these MMAs retire
           umma_commit_all<NCTA>(tfull_bar + buf);       // accumulator complete
-          if (buf) tphase1 ^= 1; else tphase0 ^= 1;
           buf = nbuf; stage = nstage; phase = nphase;
         }
       }
@@ -437,8 +504,7 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     const int jb = WIN ? 0 : (jm < tg.n_jobs ? tg.job[jm] : -1);
     const int qy = qy0 + (rm >> p.qw_shift), qx = qx0 + (rm & (p.QW - 1));
     const bool qvalid = jb >= 0 && qy < qH && qx < qW;
-    const uint32_t tempty_l0 = NCTA == 2 ? map_to_rank(smem_u32(tempty_bar + 0), 0) : 0u;   // the leader's barriers
-    const uint32_t tempty_l1 = NCTA == 2 ? map_to_rank(smem_u32(tempty_bar + 1), 0) : 0u;
+    const uint32_t tempty_leader = NCTA == 2 ? map_to_rank(smem_u32(tempty_bar), 0) : 0u;   // the leader's barriers
     {
       // both query parts -> tensor memory, two fp16 channels per 32-bit cell (lower channel in the low half).  The four
       // warps that share a TMEM lane quarter split the channels: 16 cells (64 B of the row) per tcgen05.st.
@@ -465,116 +531,111 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     }
     TopK<K> top;
     top.init();
-    int buf = 0;
-    uint32_t tph0 = 0, tph1 = 0;
-    int box_seq = 0;
-    const int n_rows = (p.BH + EPI_WG - 1) / EPI_WG;       // key rows of a box per warpgroup: wg, wg + 4
-    const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16);
-    for (int e = e_hi - 1; e >= e_lo; --e) {           // newest memory frame first: thresholds rise early
-      const int raw = p.ent[e];
-      const bool masked = WIN || !(raw & FGVC_MEM_UNMASKED);
-      const int li = masked ? 0 : 1;
-      const int nb = nbox[li];
-      int upos_e, cy = qy, cx = qx;
-      if (WIN) {
-        upos_e = qvalid ? e - p.job.mem_begin : -1;
-        // this lane's window centre in this memory entry: scale * (coarse arg-max key)   (local_attention.py:835-845)
-        if (qvalid) {
-          const int bq = max(__ldg(p.best + (int64_t)(e - p.job.mem_begin) * nq_c + qy * p.WQ + qx), 0) % nq_c;
-          cy = (bq / p.WQ) * p.scale;
-          cx = (bq % p.WQ) * p.scale;
-        }
-      } else if (p.tgroups) {
-        upos_e = qvalid ? p.upos[4 * e + jm] : -1;     // warp-uniform up to the image border
-      } else {
-        upos_e = qvalid ? e - tg.u_begin : -1;
-      }
-      const bool mine = upos_e >= 0;                       // does this lane's job have this memory entry at all?
-      const int pos_base = upos_e * p.n_pix;
-      for (int b = 0; b < nb; ++b) {
-        const uint32_t bb = boxes[li * MAX_BOXES + b];
-        const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
-        // 16-bit interval masks of the in-mask, in-image keys of this warpgroup's key rows
-        uint32_t bits[2] = {0u, 0u};
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int row = wg + EPI_WG * rr;
-          const int ky = by + row;
-          if (rr < n_rows && row < p.BH && mine && ky < p.H) {
-            int lo = 0, hi = p.W - 1;
-            if (masked) {
-              const int ady = abs(ky - cy);
-              int hw;
-              if (WIN) hw = ady <= p.rf ? p.rf : -1;
-              else hw = ady <= p.reach ? halfw[ady] : -1;
-              lo = hw < 0 ? 1 : max(cx - hw, 0);
-              hi = hw < 0 ? 0 : min(cx + hw, p.W - 1);
-            }
-            lo = max(lo - bx, 0);
-            hi = min(hi - bx, 15);
-            if (hi >= lo) bits[rr] = (2u << hi) - (1u << lo);
+    volatile float* thr_mine = thr_sh + m * EPI_WG + wg;
+    *thr_mine = -INFINITY;
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
+    // Warpgroup wg owns the key rows wg (and wg + 4 when a box has 8 rows) of every box: a static assignment, so the
+    // order in which a query's candidates reach its lists -- and with it the choice among exactly tied values -- does
+    // not depend on timing.  (Drawing row tickets from a shared counter balanced the warps a little better, 7.35 ->
+    // 7.09 ms on the bench clip, but made tied results vary from run to run: profiles/r2_b_epilogue.md.)
+    const int hw_n = WIN ? p.rf : p.reach;                 // halfw[0 .. hw_n], halfw[hw_n + 1] = -1
+    const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(wg * 16);
+    auto run = [&](auto rows_c) {
+      constexpr int ROWS = decltype(rows_c)::value;        // key rows of a box per thread
+      uint32_t buf = 0, tpar = 0, seq = 0;                 // accumulator of the next box; bit b = parity of its "full" phase
+      for (int e = e_hi - 1; e >= e_lo; --e) {           // newest memory frame first: thresholds rise early
+        const int raw = p.ent[e];
+        const bool masked = WIN || !(raw & FGVC_MEM_UNMASKED);
+        const int li = masked ? 0 : 1;
+        const int nb = nbox[li];
+        const uint32_t* blist = boxes + li * MAX_BOXES;
+        int upos_e, cy = qy, cx = qx;
+        if constexpr (WIN) {
+          upos_e = qvalid ? e - p.job.mem_begin : -1;
+          // this lane's window centre in this memory entry: scale * (coarse arg-max key)   (local_attention.py:835-845)
+          if (qvalid) {
+            const int bq = max(__ldg(p.best + (int64_t)(e - p.job.mem_begin) * nq_c + qy * p.WQ + qx), 0) % nq_c;
+            cy = (bq / p.WQ) * p.scale;
+            cx = (bq % p.WQ) * p.scale;
           }
+        } else if (p.tgroups) {
+          upos_e = qvalid ? p.upos[4 * e + jm] : -1;     // warp-uniform up to the image border
+        } else {
+          upos_e = qvalid ? e - tg.u_begin : -1;
         }
-        const bool dump = !WIN && p.dbg != nullptr && box_seq < p.dbg_max_boxes;
-        bool doit[2];
+        const bool mine = upos_e >= 0;                     // does this lane's job have this memory entry at all?
+        const int pos_base = upos_e * p.n_pix;
+        for (int b = 0; b < nb; ++b) {
+          const uint32_t bb = blist[b];
+          const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
+          // 16-bit interval masks of the in-mask, in-image keys of this thread's key rows: the half width at
+          // |ky - cy| comes from the table (-1 = row out of reach; unmasked entries: the whole row)
+          uint32_t bits[ROWS];
+          bool hot[ROWS];
+          const bool dump = !WIN && p.dbg != nullptr && (int)seq < p.dbg_max_boxes;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-          doit[rr] = rr < n_rows && (__any_sync(0xffffffffu, bits[rr] != 0) || (dump && wg + EPI_WG * rr < p.BH)) &&
-                     !(p.exp_flags & 2);                   // warp-uniform
-        mbar_wait_sleep(tfull_bar + buf, buf ? tph1 : tph0);
-        tc_fence_after();
-        uint32_t r0[16], r1[16];
-        const uint32_t taddr = lane_base + (uint32_t)(buf * 128 + wg * 16);
-        if (doit[0]) tmem_ld16_issue(taddr, r0);
-        if (doit[1]) tmem_ld16_issue(taddr + 16 * EPI_WG, r1);
-        if (doit[0]) tmem_ld_wait(r0);
-        if (doit[1]) { if (doit[0]) reg_fence16(r1); else tmem_ld_wait(r1); }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {                                   // accumulator is in registers: hand the tile back
-          if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_l1 : tempty_l0); else mbar_arrive(tempty_bar + buf);
-        }
-        if (buf) tph1 ^= 1; else tph0 ^= 1;
-        buf ^= 1;
+          for (int rr = 0; rr < ROWS; ++rr) {
+            const int row = wg + EPI_WG * rr;
+            const int ky = by + row;
+            int hw = p.W;
+            if (masked) hw = halfw[min(abs(ky - cy), hw_n + 1)];
+            const int lo = max(max(cx - hw, 0) - bx, 0);
+            const int hi = min(min(cx + hw, p.W - 1) - bx, 15);
+            const bool ok = row < p.BH;
+            bits[rr] = (ok && mine && hw >= 0 && hi >= lo && ky < p.H) ? ((2u << hi) - (1u << lo)) : 0u;
+            hot[rr] = ok && (__any_sync(0xffffffffu, bits[rr] != 0) || dump) && !(p.exp_flags & 2);   // warp-uniform
+          }
+          mbar_wait_sleep(tfull_bar + buf, (tpar >> buf) & 1u);
+          tc_fence_after();
+          uint32_t r[ROWS][16];
+          const uint32_t taddr = lane_base + buf * acc_cols;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          if (!doit[rr]) continue;
-          const uint32_t* r = rr ? r1 : r0;
-          const int row = wg + EPI_WG * rr;
-          float v[16];
+          for (int rr = 0; rr < ROWS; ++rr)
+            if (hot[rr]) tmem_ld16_issue(taddr + 16 * EPI_WG * rr, r[rr]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int rr = 0; rr < ROWS; ++rr) reg_fence16(r[rr]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {                                 // accumulator is in registers: hand the tile back
+            if (NCTA == 2) mbar_arrive_cluster(tempty_leader + 8u * buf); else mbar_arrive(tempty_bar + buf);
+          }
           if (dump) {
-            float* d = p.dbg + ((int64_t)box_seq * 128 + m) * 128 + row * 16;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = v[j] * FGVC_F16_ACC_INV;
-            if (p.dbg_meta != nullptr && m == 0 && row == 0) {
-              p.dbg_meta[4 * box_seq + 0] = e; p.dbg_meta[4 * box_seq + 1] = by;
-              p.dbg_meta[4 * box_seq + 2] = bx; p.dbg_meta[4 * box_seq + 3] = N;
+            for (int rr = 0; rr < ROWS; ++rr) {
+              if (!hot[rr]) continue;
+              const int row = wg + EPI_WG * rr;
+              float* d = p.dbg + ((int64_t)seq * 128 + m) * 128 + row * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) d[j] = __uint_as_float(r[rr][j]) * FGVC_F16_ACC_INV;
+              if (p.dbg_meta != nullptr && m == 0 && row == 0) {
+                p.dbg_meta[4 * seq + 0] = e; p.dbg_meta[4 * seq + 1] = by;
+                p.dbg_meta[4 * seq + 2] = bx; p.dbg_meta[4 * seq + 3] = N;
+              }
             }
           }
-          // candidates = in-mask elements above the running K-th value (values stay in accumulator units, x256)
-          const float thr0 = (p.exp_flags & 1) ? INFINITY : top.thr();
-          uint32_t cand = 0;
+          tpar ^= 1u << buf;
+          buf = (buf + 1 == (uint32_t)n_acc) ? 0u : buf + 1;
+          ++seq;
+          if (p.exp_flags & 1) continue;
+          // The K-th value of ANY partial list of this query bounds the final K-th value from below, so no list
+          // needs candidates under the largest of them: the warpgroups publish theirs when it changes (a stale value
+          // is only a weaker bound).  Without this each of the lists climbs to the final threshold on its own.
+          float floor_ = -INFINITY;
+          if (!(p.exp_flags & 8)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) cand |= (v[j] > thr0) ? (1u << j) : 0u;
-          cand &= bits[rr];
-          // Insert candidates in warp-wide rounds: in every round each lane that still has a
-          // candidate takes its next one, so a round serves ~4 lanes at once instead of one
-          // divergent insertion per (lane, element).
-          const int kbase = pos_base + (by + row) * p.W + bx;
-          while (__any_sync(0xffffffffu, cand != 0)) {
-            if (cand) {
-              const int j = __ffs(cand) - 1;
-              cand &= cand - 1;
-              const float x = select16(v, j);
-              if (x > top.thr()) top.push(x, kbase + j);
-            }
+            for (int w2 = 0; w2 < EPI_WG; ++w2) floor_ = fmaxf(floor_, thr_mine[w2 - wg]);
           }
+          const float thr_before = top.thr();
+          const int kbase = pos_base + (by + wg) * p.W + bx;
+#pragma unroll
+          for (int rr = 0; rr < ROWS; ++rr)
+            if (hot[rr]) scan_row<K>(r[rr], bits[rr], top, kbase + EPI_WG * rr * p.W, floor_, p.exp_flags & 16);
+          if (top.thr() != thr_before) *thr_mine = top.thr();
         }
-        ++box_seq;
       }
-    }
+    };
+    if (p.BH <= EPI_WG) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});
     // ---- merge the partial lists of the warpgroups through the (now idle) ring
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     float* mv = reinterpret_cast<float*>(ring);
@@ -635,11 +696,11 @@ static int make_map16(CUtensorMap* map, const void* bank, int n_slots, int H, in
 }
 
 // all MMAs are TS-form: a box costs ~N plus a small fixed hand-shake.  Pair tiles stage BH / 2 rows per CTA: BH even.
-static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 12); }
+static int box_cost16(int rows, int bh) { return cdiv(rows, bh) * (16 * bh + 24); }
 static int pick_bh16(int rows, int ncta) {
-  const int max_bh = MAX_NC / 16 * ncta;
+  const int max_bh = MAX_NC / 16 * ncta;       // powers of two: the epilogue splits row tickets with a shift
   int best = max_bh;
-  for (int bh = max_bh - ncta; bh >= ncta; bh -= ncta)
+  for (int bh = max_bh / 2; bh >= ncta; bh /= 2)
     if (box_cost16(rows, bh) < box_cost16(rows, best)) best = bh;
   return best;
 }
@@ -660,6 +721,17 @@ static int launch_k(const CUtensorMap& mk, const void* bank, const Params& p, di
   cfg.numAttrs = 1;
   FGVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mk, reinterpret_cast<const __half*>(bank), p));
   FGVC_LAUNCH_CHECK();
+#ifdef FGVC_TC16_STATS
+  if (p.exp_flags & 16) {      // experiment: print and reset the scan counters (synchronises!)
+    unsigned long long h[8] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_stats, sizeof(h));
+    fprintf(stderr, "[tc16 stats] grid=(%u,%u,%u) row_scans=%llu hot_rows=%llu rounds=%llu pushes=%llu\n", grid.x, grid.y,
+            grid.z, h[0], h[1], h[2], h[3]);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+  }
+#endif
   return FGVC_OK;
 }
 template <int NCTA, bool WIN>
@@ -727,7 +799,8 @@ static int launch_k1(const void* bank, int n_slots, int H, int W, int C, const f
     block_shape(H, W, p.reach, 128 / jobs_per_tile, 1, &p.QH, &p.QW, &p.BH);
   }
   static const int force_bh = getenv("FGVC_TC16_BH") ? atoi(getenv("FGVC_TC16_BH")) : 0;   // timing experiments only
-  if (force_bh >= ncta && force_bh <= MAX_NC / 16 * ncta && force_bh % ncta == 0) p.BH = force_bh;
+  if (force_bh >= ncta && force_bh <= MAX_NC / 16 * ncta && (force_bh & (force_bh - 1)) == 0) p.BH = force_bh;
+  p.bh_shift = ilog2(p.BH);
   p.qw_shift = ilog2(p.QW);
   p.lpj_shift = ilog2(128 * ncta / jobs_per_tile);
   p.lists_per_job = lists_per_job; p.split = split; p.k_out = K;
@@ -803,11 +876,13 @@ int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, i
   else { p.QH = 8; p.QW = 16; p.qw_shift = 4; }
   p.lpj_shift = 7;
   p.BH = MAX_NC / 16;
+  p.bh_shift = ilog2(p.BH);
   p.k_out = K;
   p.chunks = chunks;
   p.tiles_x = cdiv(Wc, p.QW);
   p.job = job; p.ent = mem_feat; p.best = best; p.tv = tv; p.ti = ti;
   // worst case (scattered arg-max keys): the entry lists every box of the frame
+  FGVC_CHECK_ARG(rf >= 0 && rf <= 126, "c2f window engine: radius_fine %d too large", rf);
   if ((int64_t)cdiv(Hf, p.BH) * cdiv(Wf, 16) > 2 * MAX_BOXES) {
     set_error("c2f window engine: a %dx%d map exceeds %d key boxes", Hf, Wf, 2 * MAX_BOXES);
     return FGVC_ERR_UNSUPPORTED;

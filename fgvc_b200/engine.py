@@ -316,7 +316,7 @@ def tile_shape(H, W, radius, mode, J):
     return qh.value, qw.value, bh.value, nc.value
 
 
-BOX_FIXED = 12        # per-box hand-shake of the engine in key units (csrc/topk_tc16.cu: box_cost16)
+BOX_FIXED = 24        # per-box hand-shake of the engine in key units (csrc/topk_tc16.cu: box_cost16)
 TILE_SETUP = 160      # per (tile, tile group) set-up in key units: barriers, TMEM, query rows, box lists, list merge
 
 

@@ -224,49 +224,50 @@ def masked_attention_efficient_c2f(query, key, query_fine, key_fine, value, mask
 
 
 # ------------------------------------------------------------------------------------------------
-# Legacy VFS-style utilities (mmpt/models/common/affinity_utils.py:6-73).  Nothing in the reference
-# calls them; they are kept importable with the same signatures and semantics ("subtract the k-th
-# largest, clamp, L1-renormalise" top-k, unlike the path above).  Plain device-agnostic torch ops:
-# they are API surface, not part of the accelerated hot path.
+# Legacy dense-affinity utilities of the reference's API surface (mmpt/models/common/affinity_utils.py:6-73;
+# SURVEY.md section 8 row a11).  Nothing in the reference calls them and they are not part of the accelerated path:
+# plain torch tensor algebra on whatever device the inputs live on, written from the semantics:
+#   compute_affinity : A[b, i, j] = <src[b, :, i], dst[b, :, j]> / temperature over flattened pixels, -inf where the
+#                      mask is off, optional soft-max along `softmax_dim`; fully masked lines give 0, not NaN
+#   propagate*       : out[b, c, j] = sum_i img[b, c, i] * A'[b, i, j], where with `topk` every column j of A keeps
+#                      only what exceeds its k-th largest source entry, re-normalised to unit L1 mass
+def _pixels(x):
+    """[B, C, *spatial] -> [B, C, n]"""
+    return x.flatten(2)
+
+
 def compute_affinity(src_img, dst_img, temperature=1., normalize=True, softmax_dim=None, mask=None):
-    batches, channels = src_img.shape[:2]
-    src_feat = src_img.reshape(batches, channels, -1)
-    dst_feat = dst_img.reshape(batches, channels, -1)
+    src, dst = _pixels(src_img), _pixels(dst_img)
     if normalize:
-        src_feat = torch.nn.functional.normalize(src_feat, p=2, dim=1)
-        dst_feat = torch.nn.functional.normalize(dst_feat, p=2, dim=1)
-    affinity = torch.bmm(src_feat.permute(0, 2, 1).contiguous(), dst_feat.contiguous()) / temperature
+        src, dst = (torch.nn.functional.normalize(t, p=2, dim=1) for t in (src, dst))
+    scores = torch.einsum("bci,bcj->bij", src, dst) / temperature
     if mask is not None:
-        affinity = affinity.masked_fill(~mask.bool(), float("-inf"))
+        scores = torch.where(mask.bool(), scores, scores.new_full((), float("-inf")))
     if softmax_dim is not None:
-        affinity = affinity.softmax(dim=softmax_dim)
+        scores = torch.softmax(scores, dim=softmax_dim)
     if mask is not None:
-        affinity = torch.nan_to_num(affinity, nan=0.0)
-    return affinity
+        scores = torch.nan_to_num(scores, nan=0.0)       # a line without any allowed entry soft-maxes to NaN
+    return scores
 
 
-def _legacy_topk(affinity, topk, shape):
-    kth = affinity.topk(dim=1, k=topk)[0][:, topk - 1].view(*shape)
-    affinity = (affinity - kth).clamp(min=0)
-    return affinity / affinity.sum(keepdim=True, dim=1).clamp(min=1e-12)
+def _keep_above_kth(weights, k):
+    """per column (dim 1 = source pixels): subtract the k-th largest entry, drop what is not above it, unit L1 mass"""
+    kth = torch.kthvalue(weights, weights.shape[1] - k + 1, dim=1, keepdim=True).values
+    excess = torch.relu(weights - kth)
+    return excess / excess.sum(dim=1, keepdim=True).clamp_min(1e-12)
 
 
 def propagate(img, affinity, topk=None):
-    batches, channels, height, width = img.size()
-    if topk is not None:
-        affinity = _legacy_topk(affinity, topk, (batches, 1, height * width))
-    new_img = torch.bmm(img.reshape(batches, channels, -1), affinity.contiguous())
-    return new_img.reshape(batches, channels, height, width)
+    weights = affinity if topk is None else _keep_above_kth(affinity, topk)
+    return torch.einsum("bci,bij->bcj", _pixels(img), weights).reshape(img.shape)
 
 
 def propagate_temporal(imgs, affinities, topk=None):
-    batches, channels, clip_len, height, width = imgs.size()
-    assert affinities.size(0) == batches
-    assert affinities.size(1) == clip_len
-    assert affinities.size(2) == height * width
-    assert affinities.size(2) == affinities.size(3)
-    affinities = affinities.reshape(batches, clip_len * height * width, height * width)
+    B, C, T, H, W = imgs.shape
+    if tuple(affinities.shape) != (B, T, H * W, H * W):
+        raise AssertionError(f"affinities {tuple(affinities.shape)} do not match imgs {tuple(imgs.shape)}: "
+                             f"expected {(B, T, H * W, H * W)}")
+    weights = affinities.reshape(B, T * H * W, H * W)        # every (frame, pixel) of the clip is a source
     if topk is not None:
-        affinities = _legacy_topk(affinities, topk, (batches, 1, height * width))
-    new_imgs = torch.bmm(imgs.reshape(batches, channels, -1), affinities)
-    return new_imgs.reshape(batches, channels, height, width)
+        weights = _keep_above_kth(weights, topk)
+    return torch.einsum("bci,bij->bcj", _pixels(imgs), weights).reshape(B, C, H, W)

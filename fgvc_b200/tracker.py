@@ -37,6 +37,14 @@ class VanillaTracker(nn.Module):
     def __init__(self, backbone, head=None, train_cfg=None, test_cfg=None, init_cfg=None):
         super().__init__()
         self.backbone = build_backbone(backbone)
+        # The reference runs self.head(x) in extract_feat when a head is configured and concatenates every block with
+        # test_cfg.all_blocks (vanilla_tracker.py:86-124).  Neither is built: fail loudly instead of silently feeding
+        # different features (the shipped eval config, res18_d1_eval, uses neither).
+        if head is not None:
+            raise NotImplementedError("VanillaTracker(head=...) is not built: the encoder side is plain PyTorch and "
+                                      "only the head-less eval configuration is mirrored")
+        if test_cfg is not None and (test_cfg.get("all_blocks", False) if hasattr(test_cfg, "get") else False):
+            raise NotImplementedError("test_cfg.all_blocks is not built")
         self.head = head
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg if hasattr(test_cfg, "get") and hasattr(test_cfg, "precede_frames") \
@@ -79,10 +87,15 @@ class VanillaTracker(nn.Module):
         return torch.cat(outs, dim=0)
 
     # --------------------------------------------------------------------- propagation
+    two_phase_sharding = True      # apis.sharded_forward_test: forward_test(..., shard=(rank, world))
+
     @torch.no_grad()
-    def propagate_points(self, feats, groups, image_hw):
+    def propagate_points(self, feats, groups, image_hw, shard=None):
         """feats [T,C,Hf,Wf] (CUDA); groups: list of (t0, points_xy [P',2]).
-        Returns list of [T,P',2] float64 CUDA tensors (zeros before t0)."""
+        Returns list of [T,P',2] float64 CUDA tensors (zeros before t0).
+        ``shard=(rank, world)``: two-phase split of ONE video over the default process group: K1 runs for
+        this rank's frame range only and the top-k lists are all-gathered; the recurrent tail runs for this rank's
+        slice of every group's points and the tracks are all-gathered.  Every rank returns the full result."""
         cfg = self.test_cfg
         T, C, Hf, Wf = feats.shape
         h, w = image_hw
@@ -95,7 +108,11 @@ class VanillaTracker(nn.Module):
         if nr is None and not v1:
             raise TypeError("test_mode v2 needs neighbor_range (the reference computes neighbor_range//2)")
         unmasked_first = 0 if (cfg.get("with_first_neighbor", True) or not v1) else 1
-        temperature, flags = engine.sim_params(cfg, C, cfg.temperature, sim_mode=cfg.get("sim_mode", "dot_product"),
+        # masked_attention_efficient_v2 always uses the circular dist < radius mask and has no sim_mode
+        # (local_attention.py:392-508): a v2 config with other settings must not change the result
+        mask_mode = cfg.get("mask_mode", "circle") if v1 else "circle"
+        temperature, flags = engine.sim_params(cfg, C, cfg.temperature,
+                                               sim_mode=cfg.get("sim_mode", "dot_product") if v1 else "dot_product",
                                                normalize=cfg.get("with_norm", True))
 
         bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
@@ -111,8 +128,25 @@ class VanillaTracker(nn.Module):
         outs = []
         radius = (nr // 2) if nr is not None else 1
         shared = None
+        rank, world = shard if shard is not None else (0, 1)
         if len(table) == 0:
             lists = None
+        elif world > 1:
+            from . import apis
+            if len(groups) > 1 and os.environ.get("FGVC_NO_SHARE") != "1":
+                shared = engine.shared_pair_table(table, spans, T)
+            ktable = shared[0] if shared is not None else table
+            plan = engine.plan_k1(bank, ktable, radius, cfg.topk, mask_mode, engine=self.engine_id,
+                                  groups=shared[1] if shared is not None else None, pack=shared is None)
+            lo, hi, per = apis.frame_shard(len(ktable), rank, world)
+            lists = engine.TopKLists(per * world, plan.lists_per_job, Hf * Wf, cfg.topk, dev)
+            if hi > lo:
+                engine.affinity_topk(bank, ktable, radius, cfg.topk, mask_mode, engine=self.engine_id, lists=lists,
+                                     job_range=(lo, hi), plan=plan)
+            apis.gather_job_lists(lists.val, per, rank, world)
+            apis.gather_job_lists(lists.idx, per, rank, world)
+            if shared is not None:
+                pair_ref = torch.tensor(shared[2], dtype=torch.int32, device=dev)
         else:
             # several groups: the label-independent K1 work is shared between the groups (one list per
             # (query frame, memory frame) pair); FGVC_NO_SHARE=1 keeps one K1 job per (group, frame)
@@ -120,26 +154,32 @@ class VanillaTracker(nn.Module):
                 shared = engine.shared_pair_table(table, spans, T)
             if shared is not None:
                 utable, gmax, pair_ref = shared
-                lists = engine.affinity_topk(bank, utable, radius, cfg.topk, cfg.get("mask_mode", "circle"), groups=gmax,
+                lists = engine.affinity_topk(bank, utable, radius, cfg.topk, mask_mode, groups=gmax,
                                              engine=self.engine_id, pack=False)
                 pair_ref = torch.tensor(pair_ref, dtype=torch.int32, device=dev)
             else:
-                lists = engine.affinity_topk(bank, table, radius, cfg.topk, cfg.get("mask_mode", "circle"),
-                                             engine=self.engine_id)
+                lists = engine.affinity_topk(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id)
         jobs_dev, _, mem_label = table.device(dev) if len(table) else (None, None, None)
         jobs_host = torch.tensor(table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
         # coordinates of the query frames (soft-argmax of the analytic gaussian, :321-343): one launch for all groups
         all_pts = torch.cat([pts.to(device=dev, dtype=torch.float32) for _, pts in groups], dim=0) if groups else None
         all_c0 = engine.gaussian_coords(all_pts, (h, w)) if groups and all_pts.shape[0] else None
         p_off = 0
+        sizes = [int(pts.shape[0]) for _, pts in groups]
         for (j0, t0), (_, pts) in zip(spans, groups):
-            P = pts.shape[0]
-            pts = all_pts[p_off:p_off + P]
+            P_all = pts.shape[0]
+            lo_p, hi_p = (0, P_all) if world == 1 else ((P_all * rank) // world, (P_all * (rank + 1)) // world)
+            P = hi_p - lo_p
+            pts = all_pts[p_off + lo_p:p_off + hi_p]
+            c0 = all_c0[p_off + lo_p:p_off + hi_p] if all_c0 is not None else None
+            p_off += P_all
+            if P == 0:
+                outs.append(torch.zeros(T, 0, 2, dtype=torch.float64, device=dev))
+                continue
             labels = LabelBank(T, P, Hf, Wf, dev)
             labels.put_gaussians(pts, t0, stride)
             coords = torch.zeros(T, P, 2, dtype=torch.float32, device=dev)
-            coords[t0] = all_c0[p_off:p_off + P]
-            p_off += P
+            coords[t0] = c0
             if T - t0 > 1:
                 scratch = torch.empty(T, P, Hf, Wf, dtype=torch.float32, device=dev)   # NCHW maps of every frame
                 if shared is not None:
@@ -156,10 +196,19 @@ class VanillaTracker(nn.Module):
                               _lib.ptr(coords), *engine.chain_workspace(dev, T - t0 - 1, Hf * Wf, lists.K, flags),
                               _lib.stream_ptr())
             outs.append(coords.double())
+        if world > 1:
+            from . import apis
+            pads = [-(-n // world) for n in sizes]
+            local = torch.zeros(T, sum(pads), 2, dtype=torch.float64, device=dev)
+            off = 0
+            for o, pad in zip(outs, pads):
+                local[:, off:off + o.shape[1]] = o
+                off += pad
+            outs = apis.gather_point_tracks(local, sizes, rank, world)
         return outs
 
     def forward_test(self, rgbs, query_points, trajectories, visibilities, save_image=False, save_path=None,
-                     iteration=None):
+                     iteration=None, shard=None):
         """rgbs [1,T,3,h,w]; query_points [1,P,3] (t,x,y); trajectories [1,T,P,2];
         visibilities [1,T,P].  Returns the reference's 5-tuple
         (traj_gt, vis_gt, traj_pred, vis_pred, query_points), re-ordered by query frame
@@ -173,13 +222,13 @@ class VanillaTracker(nn.Module):
         h, w = rgbs.shape[-2:]
         feats = self.get_feats(rgbs[0])
         if not self.test_cfg.get("with_first", False):
-            traj = self.propagate_points(feats, [(0, query_points[0, :, 1:])], (h, w))[0]
+            traj = self.propagate_points(feats, [(0, query_points[0, :, 1:])], (h, w), shard=shard)[0]
             return trajectories, visibilities, traj[None], torch.zeros_like(visibilities), query_points
         qt = query_points[0, :, 0]
         ts = torch.unique(qt).tolist()
         order = [torch.nonzero(qt == t).flatten() for t in ts]
         groups = [(int(t), query_points[0, idx, 1:]) for t, idx in zip(ts, order)]
-        trajs = self.propagate_points(feats, groups, (h, w))
+        trajs = self.propagate_points(feats, groups, (h, w), shard=shard)
         perm = torch.cat(order)
         pred = torch.cat(trajs, dim=1).to(trajectories.dtype)[None]
         return (trajectories[:, :, perm], visibilities[:, :, perm], pred, torch.zeros_like(visibilities),

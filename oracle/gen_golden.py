@@ -11,21 +11,9 @@ import numpy as np
 import torch
 
 from . import ref_loader
+from .inputs import coherent_feats as _coherent_feats, seeded_cfg3_inputs
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-
-
-def _coherent_feats(g, T, C, H, W, relu=True):
-    """temporally coherent, spatially smooth features (near-ties like encoder output)."""
-    base = torch.randn(C, H // 2 + 2, W // 2 + 2, generator=g)
-    frames = []
-    for t in range(T):
-        base = base + 0.15 * torch.randn(base.shape, generator=g)
-        f = torch.nn.functional.interpolate(base[None], size=(H, W), mode="bilinear",
-                                            align_corners=False)[0]
-        f = f + 0.05 * torch.randn(f.shape, generator=g)
-        frames.append(f.relu() if relu else f)
-    return torch.stack(frames)  # [T,C,H,W]
 
 
 def gen_propagate(ref):
@@ -60,6 +48,18 @@ def gen_propagate(ref):
                             v=v.numpy(), neighbor_range=nr, topk=k, non_mask_len=nml,
                             temperature=0.07, out_v1=o1.numpy(), out_v2=o2.numpy())
     return cases
+
+
+def gen_cfg3_geometry(ref):
+    """One frame at the reference eval geometry of BASELINE configs 3 / 5 (256^2 image, stride 2: 128 x 128,
+    neighbor_range 30, 6 memory entries, C = 256) through the genuine masked_attention_efficient
+    (local_attention.py:267).  Only the output and input checksums are stored."""
+    q, kf, v = seeded_cfg3_inputs()
+    mask = ref.spatial_neighbor(1, 128, 128, neighbor_range=30, device="cpu", dtype=torch.float32)
+    o = ref.masked_attention_efficient(q, kf, v, mask, temperature=0.07, topk=10, step=512)
+    np.savez_compressed(os.path.join(OUT, "prop_cfg3_128.npz"), seed=303, neighbor_range=30, topk=10,
+                        temperature=0.07, q_sum=float(q.double().sum()), k_sum=float(kf.double().sum()),
+                        v_sum=float(v.double().sum()), out=o.numpy())
 
 
 def gen_dense(ref):
@@ -185,6 +185,7 @@ def main():
     ref = ref_loader.load_functions()
     print("propagate:", gen_propagate(ref))
     gen_dense(ref)
+    gen_cfg3_geometry(ref)
     gen_masks(ref)
     gen_c2f(ref)
     gen_legacy(ref)

@@ -317,6 +317,53 @@ def test_point_sharded_forward_test_world2_gloo(with_first):
     assert res == [(0, True), (1, True)]
 
 
+def _two_phase_worker(rank, world, port, q):
+    """host side of the two-phase split of one long video (apis.frame_shard / gather_job_lists / gather_point_tracks):
+    phase 1 = every rank fills the lists of its frame range, phase 2 = every rank tracks its slice of every group."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ok = True
+    for n_jobs in (7, 2, 1):
+        lo, hi, per = apis.frame_shard(n_jobs, rank, world)
+        buf = torch.full((per * world, 3, 5), -1.0)
+        for j in range(lo, hi):
+            buf[j] = float(j)                                  # "K1" of job j
+        apis.gather_job_lists(buf, per, rank, world)
+        ok &= all(bool((buf[j] == float(j)).all()) for j in range(n_jobs))
+    sizes, T = [5, 1, 4, 0], 3
+    pads = [-(-n // world) for n in sizes]
+    local = torch.zeros(T, sum(pads), 2, dtype=torch.float64)
+    off = 0
+    for g, (n, pad) in enumerate(zip(sizes, pads)):
+        plo, phi = apis.point_shard(n, rank, world)
+        for i in range(plo, phi):                              # "track" of point i of group g
+            local[:, off + i - plo, 0] = 100 * g + i
+            local[:, off + i - plo, 1] = torch.arange(T, dtype=torch.float64)
+        off += pad
+    outs = apis.gather_point_tracks(local, sizes, rank, world)
+    for g, (n, o) in enumerate(zip(sizes, outs)):
+        ok &= tuple(o.shape) == (T, n, 2)
+        ok &= bool((o[:, :, 0] == (100 * g + torch.arange(n, dtype=torch.float64))[None]).all())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_phase_long_video_split_world2_gloo():
+    assert apis.frame_shard(7, 0, 2) == (0, 4, 4) and apis.frame_shard(7, 1, 2) == (4, 7, 4)
+    assert apis.frame_shard(1, 1, 2) == (1, 1, 1) and apis.frame_shard(0, 0, 2) == (0, 0, 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_phase_worker, args=(r, 2, 29541, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
 def test_plan_chunks_cover_all_jobs_with_full_waves():
     for n, tiles in ((63, 56), (49, 128), (5, 56), (1, 56), (249, 128)):
         ch = engine.plan_chunks(n, tiles)

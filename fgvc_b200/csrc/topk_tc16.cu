@@ -768,12 +768,14 @@ bool tc16_supported(int H, int W, int C, int K) {
   return C % 64 == 0 && C >= 64 && C <= 256 && K >= 1 && K <= 16 && H >= 1 && W >= 1;
 }
 
-// CTA pairs need >= 2 key rows per box and are only worth their wider tiles on maps with enough tiles
+// CTA pairs (cta_group::2) halve the L2 -> shared-memory bytes per MAC, but a 256-row tile has a larger pixel block
+// per job and so a larger halo (bench clip: 2.82x the in-mask pairs against 2.41x for single-CTA tiles).  Measured
+// (profiles/r2_b_epilogue.md) K1 is bound by the epilogue's candidate scan, not by the L2 fabric, so pairs do not pay
+// yet: they are built and tested, and selected with FGVC_TC16_PAIR=1.
 static bool use_pairs(int H, int W, int jobs_per_tile) {
   const int force = getenv("FGVC_TC16_PAIR") ? atoi(getenv("FGVC_TC16_PAIR")) : -1;   // experiments / tests
-  if (force == 0 || force == 1) return force == 1;
-  (void)jobs_per_tile;
-  return H >= 2 && (int64_t)H * W >= 1024;
+  (void)jobs_per_tile; (void)W;
+  return force == 1 && H >= 2;
 }
 
 // tile = jobs_per_tile jobs x (128 * ncta / jobs_per_tile) pixels.  Exposed so that the host can cost the packings

@@ -382,7 +382,11 @@ def pick_packing(table, j0, j1, H, W, radius, mode):
     if ckey in table._packed:
         return table._packed[ckey]
     best, best_cost = (1, False), None
-    for J, aligned in ((1, False), (2, False), (4, False), (2, True), (4, True)):
+    # The aligned packings issue 11 % fewer tensor MACs on a precede-20 clip, but every tile then covers ~5 memory
+    # entries instead of ~25 and K1 is bound by the epilogue's list insertions, which are most frequent while the
+    # lists are cold: measured 8.1 ms against 7.0 ms (profiles/r2_b_epilogue.md).  AUTO therefore keeps the plain
+    # packings; FGVC_PACK="4a" selects an aligned one.
+    for J, aligned in ((1, False), (2, False), (4, False)):
         if aligned and not seq:
             continue
         cost = packing_cost(table, j0, j1, H, W, radius, mode, J, aligned)
@@ -430,6 +434,9 @@ def chain_workspace(dev, n_jobs, n_pix, K, flags=0, force=False):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _CHAIN_WS[_ws_key(dev)] = ws
     return ptr(ws), nbytes
+
+
+K1_TIMING = None       # bench.py: a list -> affinity_topk appends (start, end) CUDA events of every K1 launch
 
 
 class K1Plan:
@@ -484,6 +491,20 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
     assert lists.groups == groups and lists.K == K and lists.n_jobs >= len(table), (lists.groups, plan)
     mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
     per_job = groups * lists.n_query * K * 4      # bytes of one job's lists
+    if K1_TIMING is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        try:
+            return _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job,
+                                         jobs, mem_feat, dev)
+        finally:
+            ev[1].record()
+            K1_TIMING.append(ev)
+    return _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job, jobs,
+                                 mem_feat, dev)
+
+
+def _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job, jobs, mem_feat, dev):
     # fp16 tensor engine: J consecutive jobs per query tile when that saves tensor work (csrc/topk_tc16.cu)
     if (plan.J > 1 or plan.aligned) and tensor16_ok(bank, K, engine):
         tg, uent, upos = table.packed(j0, j1, plan.J, dev, plan.aligned)

@@ -1,4 +1,4 @@
-"""Multi-GPU sanity (run under torchrun): point-sharded forward_test == single-GPU forward_test, and
+"""Multi-GPU sanity (run under torchrun): two-phase sharded forward_test == single-GPU forward_test, and
 multi_gpu_test result collection over NCCL."""
 import os
 import sys
@@ -28,6 +28,18 @@ def main():
         want = trk(test_mode=True, rgbs=rgbs, query_points=qp, trajectories=traj, visibilities=vis)
     err = (got[2].double() - want[2].double()).abs().max().item()
     same_order = torch.equal(got[4].cpu(), want[4].cpu())
+    # one group (every point queried at frame 0), more points than ranks, longer memory: the packed K1 over frame ranges
+    cfg2 = dict(cfg, precede_frames=6, with_first=False)
+    trk.test_cfg = type(trk.test_cfg)(cfg2)
+    T2, P2 = 14, 37
+    rgbs2 = S.synthetic_video(T2, h, w, seed=5)[None]
+    qp2 = S.query_points(P2, T2, h, w, seed=6, first_frame_only=True)[None]
+    with torch.no_grad():
+        got2 = apis.sharded_forward_test(trk, rgbs2, qp2, torch.zeros(1, T2, P2, 2), torch.zeros(1, T2, P2))
+        want2 = trk(test_mode=True, rgbs=rgbs2, query_points=qp2, trajectories=torch.zeros(1, T2, P2, 2),
+                    visibilities=torch.zeros(1, T2, P2))
+    err = max(err, (got2[2].double() - want2[2].double()).abs().max().item())
+    trk.test_cfg = type(trk.test_cfg)(cfg)
     # video-sharded driver + typed NCCL gather
     ds = [dict(rgbs=S.synthetic_video(4, 32, 48, seed=10 + i)[None], query_points=S.query_points(3, 4, 32, 48, seed=i)[None],
                trajectories=torch.zeros(1, 4, 3, 2), visibilities=torch.zeros(1, 4, 3)) for i in range(2 * world + 1)]

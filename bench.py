@@ -533,7 +533,52 @@ def run_secondary(dev, rank, world, args):
                          results=sweep if len(sweep) > 1 else sweep[0])
         del feats_list, feats_host
         torch.cuda.empty_cache()
+    if not args.only or "cfg3ii" in args.only:
+        res["cfg3ii_c2f_tapvid_davis"] = run_c2f_clip(dev, rank, world)
     return res
+
+
+def run_c2f_clip(dev, rank, world):
+    """BASELINE config 3-(ii): coarse-to-fine tracking of one 50-frame 256 x 256 clip per rank, 256 points, coarse
+    stride 8 (32 x 32, r = 12) + fine stride 2 (128 x 128, radius_fine 12), through fgvc_b200.C2FPointTracker."""
+    import fgvc_b200
+    from fgvc_b200 import synthetic as S
+    T, P, h, w = 50, 256, 256, 256
+    frames = S.synthetic_video(T, h, w, seed=3000 + rank).to(dev)
+    fc = S.encode(S.davis_encoder(8, seed=0).to(dev), frames, batch=8).contiguous()
+    ff = S.encode(S.davis_encoder(2, seed=0).to(dev), frames, batch=4).contiguous()
+    del frames
+    torch.cuda.empty_cache()
+    pts = S.query_points(P, T, h, w, seed=2)[:, 1:]
+    cfg = dict(precede_frames=5, topk=10, temperature=0.07, neighbor_range=24, radius_fine=12, with_first=True)
+    trk = fgvc_b200.C2FPointTracker(cfg)
+    trk.track(fc, ff, pts, (h, w))
+    torch.cuda.synchronize()
+    if world > 1:
+        _dist().barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 2
+    for _ in range(reps):
+        trk.track(fc, ff, pts, (h, w))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world) / reps
+    fc_h, ff_h = fc.cpu().pin_memory(), ff.cpu().pin_memory()
+    e0.record()
+    a, b = torch.empty_like(fc), torch.empty_like(ff)
+    a.copy_(fc_h, non_blocking=True)
+    b.copy_(ff_h, non_blocking=True)
+    traj_h = trk.track(a, b, pts, (h, w))[0].cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    return dict(coarse_hw=tuple(fc.shape[2:]), fine_hw=tuple(ff.shape[2:]), frames=T, points=P, radius_fine=12,
+                clips="1 per rank", scaling="weak", frames_per_s=(T - 1) * world / (ms / 1e3), ms_per_clip=ms,
+                e2e_frames_per_s=(T - 1) * world / (e2e_ms / 1e3),
+                ms_per_frame=ms / (T - 1), tracks_shape=list(traj_h.shape),
+                note="recurrent driver around masked_attention_efficient_c2f (fgvc_b200/c2f_tracker.py); both "
+                     "feature banks and the fine label bank stay resident across frames")
 
 
 # ------------------------------------------------------------------- CPU baseline / reference

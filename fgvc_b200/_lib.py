@@ -45,6 +45,7 @@ SIGNATURES = {
     "fgvc_labels_to_pixmajor": (I, [P, L64, I, I, P, I, I, P]),
     "fgvc_labels_to_nchw": (I, [P, I, I, I, I, P, P]),
     "fgvc_gaussian_labels": (I, [P, I, I, I, I, F, P, I, I, P]),
+    "fgvc_upsample_labels": (I, [P, I, I, I, P, I, I, I, P]),
     "fgvc_tc_supported": (I, [I, I, I, I, I]),
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
     "fgvc_affinity_topk": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),

@@ -129,6 +129,13 @@ FGVC_API int fgvc_labels_to_pixmajor(const float* src, int64_t src_chan_stride, 
 FGVC_API int fgvc_labels_to_nchw(const float* lab_bank, int32_t slot, int32_t Lp, int32_t L, int32_t n_pix,
                         float* dst, void* stream);
 
+/* Bilinear up-sampling of a pixel-major label map src[Hs*Ws][Lp] into slot `slot` of a label bank of Hd x Wd maps,
+ * with F.interpolate(mode='bilinear', align_corners=False) taps (vanilla_tracker.py:396-400 applies it to the
+ * propagated map; the coarse-to-fine clip driver uses it to turn the coarse output of
+ * masked_attention_efficient_c2f, local_attention.py:721-880, into the next frame's fine memory labels). */
+FGVC_API int fgvc_upsample_labels(const float* src, int32_t Hs, int32_t Ws, int32_t Lp, float* lab_bank, int32_t slot,
+                         int32_t Hd, int32_t Wd, void* stream);
+
 /* draw_gaussion_map_online at feature resolution (vanilla_tracker.py:204-221):
  * lab[slot][y*W+x][p] = exp(-((x*stride-px)^2 + (y*stride-py)^2) / (2 sigma^2)).
  * points_xy: [P][2] (x,y) image pixels. */

@@ -107,6 +107,23 @@ def gen_c2f(ref):
                         temperature=0.07, radius_fine=rf, out=o.numpy())
 
 
+def gen_c2f_driver(ref):
+    """The coarse-to-fine clip loop (oracle.track_clip_c2f_port) around the GENUINE masked_attention_efficient_c2f."""
+    from . import oracle as O
+    g = torch.Generator().manual_seed(17)
+    T, C, Cf, Hc, Wc, s = 5, 32, 64, 8, 10, 4
+    fc = _coherent_feats(g, T, C, Hc, Wc)
+    ff = _coherent_feats(g, T, Cf, Hc * s, Wc * s)
+    h, w = Hc * s * 2, Wc * s * 2                       # fine stride 2, coarse stride 8
+    pts = torch.tensor([[20.5, 17.25], [50.0, 40.0], [9.75, 55.5], [70.25, 8.0]])
+    cfg = dict(precede_frames=2, topk=10, temperature=0.07, neighbor_range=8, radius_fine=4, with_first=True, step=16)
+    mask = ref.spatial_neighbor(1, Hc, Wc, neighbor_range=8, device="cpu", dtype=torch.float32)
+    outs, traj = O.track_clip_c2f_port(fc, ff, pts, (h, w), cfg, c2f=ref.masked_attention_efficient_c2f, mask=mask)
+    np.savez_compressed(os.path.join(OUT, "c2f_driver.npz"), feats_c=fc.numpy(), feats_f=ff.numpy(), points=pts.numpy(),
+                        image_hw=np.array([h, w]), precede_frames=2, topk=10, temperature=0.07, neighbor_range=8,
+                        radius_fine=4, outs=torch.stack(outs).numpy(), traj=traj)
+
+
 def gen_legacy(ref):
     g = torch.Generator().manual_seed(11)
     a = torch.randn(2, 16, 5, 6, generator=g)
@@ -188,6 +205,7 @@ def main():
     gen_cfg3_geometry(ref)
     gen_masks(ref)
     gen_c2f(ref)
+    gen_c2f_driver(ref)
     gen_legacy(ref)
     gen_tracker()
     gen_tapvid_metrics()

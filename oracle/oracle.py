@@ -292,6 +292,37 @@ def track_clip_port(feats, points_xy, image_hw, cfg, propagate=None):
     return labels, np.transpose(xy, (2, 1, 0))
 
 
+def track_clip_c2f_port(feats_c, feats_f, points_xy, image_hw, cfg, c2f=None, mask=None):
+    """The coarse-to-fine clip loop of fgvc_b200/c2f_tracker.py, restated on CPU around ``c2f`` (default: c2f_port;
+    oracle/gen_golden.py passes the GENUINE masked_attention_efficient_c2f, local_attention.py:721-880).  The
+    reference has no driver for this operator: the loop is the builder's design --
+    coarse output -> bilinear x s -> fine memory labels of the next frames; coordinates from the coarse output
+    up-sampled to the image (vanilla_tracker.py:396-406).  Returns (coarse outputs [T-1][L,Hc,Wc], traj [T,P,2])."""
+    T, C, Hc, Wc = feats_c.shape
+    Hf, Wf = feats_f.shape[2:]
+    h, w = image_hw
+    full, lab0 = gaussian_labels(points_xy, h, w, h // Hf)
+    if mask is None:
+        mask = neighbor_mask(Hc, Wc, cfg["neighbor_range"], cfg.get("mask_mode", "circle"))
+    labels, preds, outs = [lab0], [full], []
+    for t in range(1, T):
+        mem = memory_frames(t, cfg["precede_frames"], cfg.get("with_first", True))
+        k = feats_c[mem].permute(1, 0, 2, 3)[None].contiguous()
+        kf = feats_f[mem].permute(1, 0, 2, 3)[None].contiguous()
+        v = torch.stack([labels[m] for m in mem], dim=1)[None].contiguous()
+        if c2f is None:
+            out = c2f_port(feats_c[t][None], k, feats_f[t][None], kf, v, mask, temperature=cfg["temperature"],
+                           topk=cfg["topk"], radius_fine=cfg.get("radius_fine", 12))["out"][0]
+        else:
+            out = c2f(feats_c[t][None], k, feats_f[t][None], kf, v, mask, temperature=cfg["temperature"],
+                      topk=cfg["topk"], step=cfg.get("step", 64), radius_fine=cfg.get("radius_fine", 12))[0]
+        outs.append(out)
+        labels.append(F.interpolate(out[None], size=(Hf, Wf), mode="bilinear", align_corners=False)[0])
+        preds.append(F.interpolate(out[None], size=(h, w), mode="bilinear", align_corners=False)[0])
+    xy = img2coord_port(torch.stack(preds).numpy())
+    return outs, np.transpose(xy, (2, 1, 0))
+
+
 def group_by_query_frame(query_points):
     """Grouping of ``forward_test`` when test_cfg.with_first is set
     (vanilla_tracker.py:246-295): ascending unique query frame; within a group the

@@ -183,3 +183,45 @@ def test_precede20_clip_through_packed_tiles_matches_oracle_loop(pack):
     assert float(err.median()) < TIGHT
     want_masks = torch.stack([O.decode_masks_port(want[t], (H * 4, W * 4)) for t in range(T)])
     assert float((masks.cpu().long() == want_masks).float().mean()) >= 0.999
+
+
+# ------------------------------------------------------------------ config 3-(ii): the coarse-to-fine clip driver
+def test_c2f_clip_driver_matches_genuine_loop(golden_dir):
+    """fgvc_b200.C2FPointTracker against the loop around the genuine masked_attention_efficient_c2f (committed
+    fixture): coarse outputs within 1e-3 (away from near-ties of the coarse arg-max), tracks within 0.5 px."""
+    import fgvc_b200
+    d = np.load(os.path.join(golden_dir, "c2f_driver.npz"))
+    cfg = dict(precede_frames=int(d["precede_frames"]), topk=int(d["topk"]), temperature=float(d["temperature"]),
+               neighbor_range=int(d["neighbor_range"]), radius_fine=int(d["radius_fine"]), with_first=True)
+    trk = fgvc_b200.C2FPointTracker(cfg)
+    h, w = (int(x) for x in d["image_hw"])
+    traj, outs = trk.track(torch.from_numpy(d["feats_c"]).cuda(), torch.from_numpy(d["feats_f"]).cuda(),
+                           torch.from_numpy(d["points"]), (h, w))
+    want = torch.from_numpy(d["outs"])                             # [T-1, L, Hc, Wc]
+    L, Hc, Wc = want.shape[1:]
+    got = torch.stack([o[:, :L].t().reshape(L, Hc, Wc) for o in outs]).cpu()
+    err = (got - want).abs().amax(dim=1).flatten()
+    assert float((err > TOL).float().mean()) <= 0.05, float(err.max())
+    assert float(err.median()) < TIGHT
+    # the 8 x 10 coarse map is up-sampled 8x: its peak is a plateau of near-equal pixels, and which five of them
+    # img2coord picks is decided by the last bit -- allow a symmetric flip (< 1 px) on the odd point
+    terr = np.abs(traj.cpu().numpy() - d["traj"]).max(axis=-1)
+    assert float((terr <= 0.5).mean()) >= 0.9 and float(terr.max()) < 1.0 and float(np.median(terr)) < 1e-3
+
+
+def test_c2f_clip_driver_cfg3_geometry_matches_oracle_loop():
+    """The config-3-(ii) geometry through the driver: 256^2 image, coarse stride 8 (32 x 32, r = 12), fine stride 2
+    (128 x 128, radius_fine 12), 256 points, precede 5, a 4-frame clip (the oracle loop costs ~2 s per frame)."""
+    import fgvc_b200
+    torch.set_num_threads(os.cpu_count() or 8)
+    g = torch.Generator().manual_seed(3302)
+    T, C, Cf, P = 4, 256, 256, 256
+    fc = _coherent(g, T, C, 32, 32)
+    ff = _coherent(g, T, Cf, 128, 128)
+    pts = torch.rand(P, 2, generator=g) * 236 + 10
+    cfg = dict(precede_frames=5, topk=10, temperature=0.07, neighbor_range=24, radius_fine=12, with_first=True)
+    _, want = O.track_clip_c2f_port(fc, ff, pts, (256, 256), cfg)
+    traj, _ = fgvc_b200.C2FPointTracker(cfg).track(fc.cuda(), ff.cuda(), pts, (256, 256))
+    err = np.abs(traj.cpu().numpy() - want).max(axis=-1)
+    assert float((err <= 0.5).mean()) >= 0.99, float((err <= 0.5).mean())
+    assert float(np.median(err)) < 1e-2

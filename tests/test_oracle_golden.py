@@ -166,3 +166,15 @@ def test_tapvid_metrics_match_reference(golden_dir, mode):
     for k in keys:
         assert np.allclose(got[k], d[f"{mode}__{k}"], atol=1e-12), k
         assert np.allclose(dev[k].numpy(), d[f"{mode}__{k}"], atol=1e-12), k
+
+
+def test_c2f_clip_loop_port_matches_genuine_operator_loop(golden_dir):
+    """oracle.track_clip_c2f_port (the driver loop of fgvc_b200/c2f_tracker.py restated around c2f_port) against the
+    same loop run around the GENUINE masked_attention_efficient_c2f (fixture written by oracle/gen_golden.py)."""
+    d = np.load(os.path.join(golden_dir, "c2f_driver.npz"))
+    cfg = dict(precede_frames=int(d["precede_frames"]), topk=int(d["topk"]), temperature=float(d["temperature"]),
+               neighbor_range=int(d["neighbor_range"]), radius_fine=int(d["radius_fine"]), with_first=True)
+    outs, traj = O.track_clip_c2f_port(torch.from_numpy(d["feats_c"]), torch.from_numpy(d["feats_f"]),
+                                       torch.from_numpy(d["points"]), tuple(int(x) for x in d["image_hw"]), cfg)
+    assert (torch.stack(outs) - torch.from_numpy(d["outs"])).abs().max() < 2e-6
+    assert np.abs(traj - d["traj"]).max() < 1e-3

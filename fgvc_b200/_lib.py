@@ -14,7 +14,13 @@ MASK_CIRCLE, MASK_SQUARE = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 BANK_TF32, BANK_F16 = 0, 1
 MEM_UNMASKED = 0x40000000
-WEIGHT_COSINE, SIM_L2, HARD_PROP = 1, 2, 4
+WEIGHT_COSINE, SIM_L2, HARD_PROP, ZERO_PAD = 1, 2, 4, 8
+
+
+def zero_pad_flags(radius, W):
+    """FGVC_ZERO_PAD_FLAGS of include/fgvc_b200.h"""
+    assert 0 < radius <= 255 and 0 < W <= 65535
+    return ZERO_PAD | (int(radius) << 8) | (int(W) << 16)
 
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3

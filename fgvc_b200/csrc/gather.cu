@@ -7,6 +7,24 @@ namespace fgvc {
 
 constexpr int QB = 64;  // queries per CTA
 
+// Local-window ("HR") propagation (HRVanillaTracker.forward_test_main, vanilla_tracker.py:547-563): the candidates of
+// a query are the (2r+1)^2 window positions of every memory frame, and the positions OUTSIDE the image are still
+// candidates -- mmcv's Correlation and F.unfold(padding=r) give them affinity 0 and value 0.  K1 lists only the real
+// keys; here the n_oob zero candidates of the query are merged analytically: they displace the negative real
+// winners from the end of the (sorted) list.  Returns how many zeros enter the top-K.
+template <int K>
+__device__ __forceinline__ int zero_pad_count(const TopK<K>& top, int k_in, int flags, int q, int n_pix, int n_mem) {
+  if (!(flags & FGVC_ZERO_PAD)) return 0;
+  const int r = (flags >> 8) & 0xff, W = (flags >> 16) & 0xffff, H = n_pix / W;
+  const int qy = q / W, qx = q - qy * W;
+  const int cy = min(qy + r, H - 1) - max(qy - r, 0) + 1, cx = min(qx + r, W - 1) - max(qx - r, 0) + 1;
+  const int n_oob = n_mem * ((2 * r + 1) * (2 * r + 1) - cy * cx);
+  int nonneg = 0;
+#pragma unroll
+  for (int i = 0; i < K; ++i) nonneg += (i < k_in && top.id[i] >= 0 && top.v[i] >= 0.f) ? 1 : 0;
+  return min(n_oob, k_in - nonneg);
+}
+
 template <int K>
 __global__ void __launch_bounds__(256)
 gather_labels_kernel(const float* __restrict__ tv, const int32_t* __restrict__ ti, int k_in, int groups,
@@ -36,29 +54,31 @@ gather_labels_kernel(const float* __restrict__ tv, const int32_t* __restrict__ t
     //   similarity  a = cos / temperature                      (dot_product, local_attention.py:321-323)
     //               a = (2 cos - 1) / sqrt(C) [= temperature]  (l2-distance on unit vectors, :324-327)
     //   weights     softmax(a) (:369)   or   clamp(a, 0)^2 ('cosine', :371)
+    const int zt = q < n_pix ? zero_pad_count<K>(top, k_in, flags, q, n_pix, job.mem_end - job.mem_begin) : 0;
     float a[K];
 #pragma unroll
     for (int i = 0; i < K; ++i)
       a[i] = (flags & FGVC_SIM_L2) ? __fdiv_rn(2.f * top.v[i] - 1.f, temperature) : __fdiv_rn(top.v[i], temperature);
-    float m = a[0], sum = 0.f;
+    float m = zt > 0 ? fmaxf(a[0], 0.f) : a[0], sum = 0.f;
     if (flags & FGVC_WEIGHT_COSINE) {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const float c = fmaxf(a[i], 0.f);
-        a[i] = (i < k_in && top.id[i] >= 0) ? c * c : 0.f;
+        a[i] = (i < k_in - zt && top.id[i] >= 0) ? c * c : 0.f;
       }
       sum = 1.f;
     } else {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        a[i] = (i < k_in && top.id[i] >= 0) ? expf(a[i] - m) : 0.f;
+        a[i] = (i < k_in - zt && top.id[i] >= 0) ? expf(a[i] - m) : 0.f;
         sum += a[i];
       }
+      sum += (float)zt * expf(0.f - m);          // the zero-padded winners: weight exp(0 / temperature), value 0
     }
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       int id = top.id[i];
-      bool ok = i < k_in && id >= 0;
+      bool ok = i < k_in - zt && id >= 0;
       sw[tid][i] = ok ? ((flags & FGVC_WEIGHT_COSINE) ? a[i] : __fdiv_rn(a[i], sum)) : 0.f;
       int row = 0;
       if (ok) {
@@ -144,31 +164,33 @@ gather_weights_kernel(const float* __restrict__ tv, const int32_t* __restrict__ 
       }
     }
   }
+  const int zt = zero_pad_count<K>(top, k_in, flags, q, n_pix, job.mem_end - job.mem_begin);
   float a[K];
 #pragma unroll
   for (int i = 0; i < K; ++i)
     a[i] = (flags & FGVC_SIM_L2) ? __fdiv_rn(2.f * top.v[i] - 1.f, temperature) : __fdiv_rn(top.v[i], temperature);
-  const float m = a[0];
+  const float m = zt > 0 ? fmaxf(a[0], 0.f) : a[0];
   float sum = 0.f;
   if (flags & FGVC_WEIGHT_COSINE) {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       const float c = fmaxf(a[i], 0.f);
-      a[i] = (i < k_in && top.id[i] >= 0) ? c * c : 0.f;
+      a[i] = (i < k_in - zt && top.id[i] >= 0) ? c * c : 0.f;
     }
     sum = 1.f;
   } else {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      a[i] = (i < k_in && top.id[i] >= 0) ? expf(a[i] - m) : 0.f;
+      a[i] = (i < k_in - zt && top.id[i] >= 0) ? expf(a[i] - m) : 0.f;
       sum += a[i];
     }
+    sum += (float)zt * expf(0.f - m);            // the zero-padded winners: weight exp(0 / temperature), value 0
   }
   const int64_t o = ((int64_t)blockIdx.y * n_pix + q) * K;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const int id = top.id[i];
-    const bool ok = i < k_in && id >= 0;
+    const bool ok = i < k_in - zt && id >= 0;
     int row = 0;
     if (ok) {
       const int pos = id / n_pix;

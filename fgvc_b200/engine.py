@@ -658,6 +658,8 @@ class MaskClipPropagator:
                                                   normalize=cfg.get("with_norm", True))
         if cfg.get("hard_prop", False):
             self.flags |= _lib.HARD_PROP
+        if cfg.get("local_window", False):       # HRVanillaTracker: square window, zero-padded candidates
+            self.flags |= _lib.zero_pad_flags(self.radius, W)
         self.jobs_host = torch.tensor(self.table.jobs, dtype=torch.int32).reshape(-1, 4).contiguous()
 
     def _decode(self, t, masks=None):

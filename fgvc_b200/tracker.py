@@ -88,6 +88,7 @@ class VanillaTracker(nn.Module):
 
     # --------------------------------------------------------------------- propagation
     two_phase_sharding = True      # apis.sharded_forward_test: forward_test(..., shard=(rank, world))
+    local_window = False           # HRVanillaTracker: square window + zero-padded candidates
 
     @torch.no_grad()
     def propagate_points(self, feats, groups, image_hw, shard=None):
@@ -111,12 +112,19 @@ class VanillaTracker(nn.Module):
         # masked_attention_efficient_v2 always uses the circular dist < radius mask and has no sim_mode
         # (local_attention.py:392-508): a v2 config with other settings must not change the result
         mask_mode = cfg.get("mask_mode", "circle") if v1 else "circle"
+        if self.local_window:
+            mask_mode, unmasked_first = "square", 0          # (2r+1)^2 window around the query position, every frame
         temperature, flags = engine.sim_params(cfg, C, cfg.temperature,
                                                sim_mode=cfg.get("sim_mode", "dot_product") if v1 else "dot_product",
                                                normalize=cfg.get("with_norm", True))
 
+        if self.local_window:
+            if nr is None:
+                raise TypeError("the local-window tracker needs neighbor_range")
+            # window positions outside the image stay candidates (affinity 0, value 0): merged by the gather
+            flags |= _lib.zero_pad_flags(nr // 2, Wf)
         bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
-        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", True))
+        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", cfg.get("withnorm", True)))
 
         table = JobTable()
         spans = []   # per group: (first job, t0)
@@ -247,11 +255,95 @@ class VanillaTracker(nn.Module):
         return clip.run(feats.float().contiguous(), onehot)
 
 
+def nearest_resize(seg, size):
+    """``pil_nearest_interpolate`` (mmpt/models/common/utils.py:39-56) on the device: PIL's NEAREST picks the source
+    pixel floor((dst + 0.5) * in / out).  seg [H,W] integer tensor -> [size[0], size[1]]."""
+    H, W = seg.shape[-2:]
+    dev = seg.device
+    ys = ((torch.arange(size[0], device=dev, dtype=torch.float64) + 0.5) * H / size[0]).floor().clamp_(0, H - 1).long()
+    xs = ((torch.arange(size[1], device=dev, dtype=torch.float64) + 0.5) * W / size[1]).floor().clamp_(0, W - 1).long()
+    return seg[..., ys, :][..., xs]
+
+
+def pad_divide_by(x, d):
+    """mmpt/models/common/utils.py:397-412: zero-pad the last two dims symmetrically to multiples of d."""
+    h, w = x.shape[-2:]
+    nh, nw = -(-h // d) * d, -(-w // d) * d
+    lh, lw = (nh - h) // 2, (nw - w) // 2
+    pad = (lw, nw - w - lw, lh, nh - h - lh)
+    return torch.nn.functional.pad(x, pad), pad
+
+
+class HRVanillaTracker(VanillaTracker):
+    """Local-window ("HR") tracker: ``HRVanillaTracker`` of the reference (vanilla_tracker.py:415-831) without
+    mmcv.ops.Correlation.  Per frame every query pixel correlates with the (2r+1)^2 window around its own position in
+    each memory frame (r = neighbor_range // 2); window positions outside the image are candidates with affinity 0
+    and value 0; top-k over all frames, temperature after the top-k, soft-max, weighted sum (:541-563).  On the GPU
+    this is K1 with the square mask (the R^2-fold correlation volume and the unfolded labels never exist) plus the
+    analytic zero candidates in the gather (FGVC_ZERO_PAD).
+
+    ``forward_test`` is the point entry (:492-585); ``forward_test_vos`` the mask entry
+    ``forward_test_backward_save_mem(imgs, ref_seg_map, img_meta)`` (:663-831)."""
+
+    local_window = True
+
+    def __init__(self, stride=2, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.stride = stride
+        self.hard_prop = self.test_cfg.get("hard_prop", False)
+
+    @torch.no_grad()
+    def forward_test_vos(self, imgs, ref_seg_map, img_meta, save_image=False, save_path=None, iteration=None):
+        """imgs [1, n, 3, T, h, w] (or [1, 3, T, h, w]); ref_seg_map [1, h, w] integer labels of frame 0;
+        img_meta[0]['original_shape'].  Returns a list with one uint8/int array [T, H0, W0] of per-frame label
+        masks (frame 0 = the given mask), as the reference's ``list(all_seg_preds)`` for integer input."""
+        _lib.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        imgs = imgs.to(dev)
+        if imgs.ndim == 6:
+            imgs = imgs.reshape((-1,) + imgs.shape[2:])
+        assert imgs.shape[0] == 1 and ref_seg_map.ndim == 3, "one clip, integer reference mask"
+        h, w = imgs.shape[-2:]
+        imgs, _ = pad_divide_by(imgs, self.stride)
+        seg, pa = pad_divide_by(ref_seg_map.to(dev), self.stride)
+        pad_shape = tuple(seg.shape[-2:])
+        oh, ow = (int(x) for x in img_meta[0]["original_shape"][:2])
+        frames = imgs[0].transpose(0, 1).contiguous()              # [T,3,H,W]
+        feats = self.get_feats(frames)
+        T, C, Hf, Wf = feats.shape
+        small = nearest_resize(seg[0], (Hf, Wf)).long()
+        onehot = torch.nn.functional.one_hot(small).permute(2, 0, 1).float().contiguous()
+        L = onehot.shape[0]
+        first = torch.nn.functional.interpolate(ref_seg_map[None].float().to(dev), size=(oh, ow), mode="nearest")[0, 0]
+        cfg = dict(self.test_cfg)
+        cfg.update(mask_mode="square", local_window=True, with_first_neighbor=True,
+                   with_norm=self.test_cfg.get("with_norm", True))
+        direct = sum(pa) == 0 and (oh, ow) == (h, w)
+        clip = engine.MaskClipPropagator(T, C, Hf, Wf, L, (oh, ow) if direct else pad_shape, cfg, dev, self.engine_id)
+        maps, masks = clip.run(feats.float().contiguous(), onehot, want_maps=not direct)
+        if direct:
+            out = masks.clone()
+        else:
+            # padded input or a different original size: the reference's exact resize chain on the label maps
+            # (:769-798: bilinear to the padded size, un-pad, bilinear to the original size, min-max, arg-max)
+            F = torch.nn.functional
+            p = F.interpolate(maps, size=pad_shape, mode="bilinear", align_corners=False)
+            p = p[:, :, pa[2]:pad_shape[0] - pa[3], pa[0]:pad_shape[1] - pa[1]]
+            p = F.interpolate(p, size=(oh, ow), mode="bilinear", align_corners=False)
+            lo, hi = p.amin(dim=(2, 3), keepdim=True), p.amax(dim=(2, 3), keepdim=True)
+            p = torch.where(hi > 0, (p - lo) / (hi - lo + 1e-12), p)
+            out = p.argmax(dim=1).to(torch.uint8)
+        out[0] = first.to(out.dtype)
+        return [out.cpu().numpy()]
+
+
 B200VanillaTracker = VanillaTracker
+B200HRVanillaTracker = HRVanillaTracker
 
 
 def register_in_mmpt():
     """Inside an mmpt installation: make ``eval_arc='B200VanillaTracker'`` resolvable."""
     from mmpt.models.registry import MODELS
     MODELS.register_module(name="B200VanillaTracker", module=VanillaTracker)
+    MODELS.register_module(name="B200HRVanillaTracker", module=HRVanillaTracker)
     return MODELS

@@ -104,6 +104,13 @@ typedef struct fgvc_tile_group {
 #define FGVC_SIM_L2 2        /* a = (2 cos - 1) / temperature with temperature := sqrt(C)
                                 (sim_mode='l2-distance' on normalised features, local_attention.py:324-327) */
 
+/* Local-window ("HR") propagation (HRVanillaTracker.forward_test_main, vanilla_tracker.py:492-585, on
+ * mmcv.ops.Correlation + F.unfold(padding=r)): with a SQUARE mask of radius r the window positions outside the image
+ * are candidates too, with affinity 0 and value 0; the gather merges them analytically into the winners.  The flag
+ * carries the geometry: FGVC_ZERO_PAD | (r << 8) | (W << 16), r <= 255, W <= 65535. */
+#define FGVC_ZERO_PAD 8
+#define FGVC_ZERO_PAD_FLAGS(radius, W) (FGVC_ZERO_PAD | ((radius) << 8) | ((W) << 16))
+
 #define FGVC_MEM_UNMASKED 0x40000000 /* OR into mem_feat_slot: radius mask not applied
                                         (the first non_mask_len frames, local_attention.py:347) */
 

@@ -323,6 +323,72 @@ def track_clip_c2f_port(feats_c, feats_f, points_xy, image_hw, cfg, c2f=None, ma
     return outs, np.transpose(xy, (2, 1, 0))
 
 
+# ---------------------------------------------------------------- local-window ("HR") propagation
+def correlation_unfold(query, key, radius):
+    """``mmcv.ops.Correlation(max_displacement=radius)(query, key).flatten(1, 2)`` restated with F.unfold
+    (call sites vanilla_tracker.py:421-441): out[b, (dy+r)*(2r+1) + (dx+r), y, x] = <query[b,:,y,x],
+    key[b,:,y+dy,x+dx]>, zero outside the image, no normalisation.  mmcv-full 1.5.2 is not vendored and not
+    installable here, so this restatement is PARITY UNPINNED for that one op; what the tracker
+    needs from it is only that displacement i of the correlation and of F.unfold(value, padding=r) name the same key,
+    which holds for any ordering shared by both."""
+    B, C, H, W = query.shape
+    R = 2 * radius + 1
+    unf = F.unfold(key, kernel_size=(R, R), padding=radius).reshape(B, C, R * R, H * W)
+    return (unf * query.reshape(B, C, 1, H * W)).sum(1).reshape(B, R * R, H, W)
+
+
+def hr_propagate_port(query, key, value, radius, temperature=1.0, topk=10, normalize=True):
+    """One frame of ``HRVanillaTracker.forward_test_main`` (vanilla_tracker.py:541-563): correlation of the query
+    with every memory frame in a (2r+1)^2 window, top-k over K * R^2 candidates (zero-padded window positions
+    included: affinity 0, value 0), temperature after the top-k, soft-max, weighted sum of the unfolded labels.
+    query [1,C,H,W]; key [1,C,K,H,W]; value [1,L,K,H,W] -> [1,L,H,W]."""
+    C, H, W = query.shape[1:]
+    K, L = key.shape[2], value.shape[1]
+    R = 2 * radius + 1
+    if normalize:
+        query, key = _unit(query, 1), _unit(key, 1)
+    kk = key[0].transpose(0, 1)                                           # [K,C,H,W]
+    corr = correlation_unfold(query.repeat(K, 1, 1, 1), kk, radius)        # [K,R^2,H,W]
+    unfold_v = F.unfold(value[0].transpose(0, 1), kernel_size=(R, R), padding=radius).reshape(K, L, R * R, H, W)
+    corr = corr.reshape(1, K * R * R, H, W)
+    unfold_v = unfold_v.transpose(0, 1).reshape(1, L, K * R * R, H, W)
+    top_a, top_i = corr.topk(k=topk, dim=1)
+    top_v = torch.gather(unfold_v, 2, top_i.unsqueeze(1).expand(1, L, topk, H, W))
+    w = (top_a / temperature).softmax(dim=1)
+    return torch.einsum("bckhw,bkhw->bchw", top_v, w)
+
+
+def nearest_resize_port(seg, size):
+    """``pil_nearest_interpolate`` (common/utils.py:39-56: mmcv.imresize(..., 'nearest', backend='pillow')):
+    PIL's NEAREST picks source pixel floor((dst + 0.5) * in / out).  seg [H,W] integer tensor -> [size]."""
+    H, W = seg.shape
+    ys = ((torch.arange(size[0], dtype=torch.float64) + 0.5) * H / size[0]).floor().clamp(0, H - 1).long()
+    xs = ((torch.arange(size[1], dtype=torch.float64) + 0.5) * W / size[1]).floor().clamp(0, W - 1).long()
+    return seg[ys][:, xs]
+
+
+def track_masks_hr_port(feats, ref_seg, out_hw, cfg):
+    """The mask loop of ``forward_test_backward_save_mem`` (vanilla_tracker.py:663-798) from the feature bank on, for
+    an un-padded clip whose original size is ``out_hw``: nearest-resized one-hot labels (:694-705), local-window
+    propagation per frame, decode = bilinear up-sample, per-channel min-max where max > 0, arg-max (:769-798).
+    feats [T,C,Hf,Wf]; ref_seg [h,w] integer.  Returns (label maps [T,L,Hf,Wf], masks [T,h,w] long)."""
+    T, C, Hf, Wf = feats.shape
+    lab0 = onehot_labels(nearest_resize_port(ref_seg, (Hf, Wf)))
+    labels, soft = [lab0], [lab0]          # memory labels (hardened with hard_prop) / soft predictions
+    r = cfg["neighbor_range"] // 2
+    for t in range(1, T):
+        mem = memory_frames(t, cfg["precede_frames"], cfg.get("with_first", True))
+        k = feats[mem].permute(1, 0, 2, 3)[None]
+        v = torch.stack([labels[m] for m in mem], dim=1)[None]
+        lab = hr_propagate_port(feats[t][None], k, v, r, temperature=cfg["temperature"], topk=cfg["topk"],
+                                normalize=cfg.get("with_norm", True))[0]
+        labels.append(F.one_hot(lab.argmax(0), lab.shape[0]).permute(2, 0, 1).float()
+                      if cfg.get("hard_prop", False) else lab)
+        soft.append(lab)
+    masks = torch.stack([ref_seg.long()] + [decode_masks_port(s_, out_hw) for s_ in soft[1:]])
+    return torch.stack(soft), masks
+
+
 def group_by_query_frame(query_points):
     """Grouping of ``forward_test`` when test_cfg.with_first is set
     (vanilla_tracker.py:246-295): ascending unique query frame; within a group the
@@ -335,7 +401,7 @@ def group_by_query_frame(query_points):
 def onehot_labels(seg, num_classes=None):
     """int mask [Hf,Wf] -> one-hot [L,Hf,Wf] float (vanilla_tracker.py:694-705)."""
     seg = torch.as_tensor(seg).long()
-    return F.one_hot(seg, num_classes).permute(2, 0, 1).float()
+    return F.one_hot(seg, -1 if num_classes is None else num_classes).permute(2, 0, 1).float()
 
 
 def decode_masks_port(label, out_hw):

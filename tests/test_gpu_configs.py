@@ -225,3 +225,59 @@ def test_c2f_clip_driver_cfg3_geometry_matches_oracle_loop():
     err = np.abs(traj.cpu().numpy() - want).max(axis=-1)
     assert float((err <= 0.5).mean()) >= 0.99, float((err <= 0.5).mean())
     assert float(np.median(err)) < 1e-2
+
+
+# ------------------------------------------------------------------ local-window ("HR") tracker and the VOS entry
+def _hr_prop(q, k, v, mask=None, temperature=1.0, topk=10, step=None, normalize=True, non_mask_len=0, radius=None):
+    return O.hr_propagate_port(q, k, v, radius, temperature=temperature, topk=topk, normalize=normalize)
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_hr_local_window_points_match_oracle_loop(relu):
+    """fgvc_b200.HRVanillaTracker (vanilla_tracker.py:492-585) against the oracle loop around the F.unfold restatement
+    of the correlation.  Without the ReLU the affinities are signed, so near the borders the zero-padded window
+    positions (affinity 0, value 0) really enter the top-k."""
+    import functools as ft
+    import fgvc_b200
+    g = torch.Generator().manual_seed(88 + int(relu))
+    T, C, Hf, Wf, stride, nr = 6, 64, 20, 24, 2, 8
+    feats = _coherent(g, T, C, Hf, Wf)
+    if not relu:
+        feats = torch.randn(T, C, Hf, Wf, generator=g) * 0.5 + feats - feats.mean()
+    h, w = Hf * stride, Wf * stride
+    pts = torch.rand(9, 2, generator=g) * torch.tensor([w - 1.0, h - 1.0])
+    pts[0] = torch.tensor([1.0, 1.5])                       # corner points: most of their window is padding
+    pts[1] = torch.tensor([w - 2.0, h - 1.5])
+    cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=nr, with_first=True)
+    labels_want, want = O.track_clip_port(feats, pts, (h, w), dict(cfg, neighbor_range=None),
+                                          propagate=ft.partial(_hr_prop, radius=nr // 2))
+    trk = fgvc_b200.HRVanillaTracker(backbone=torch.nn.Identity(), test_cfg=cfg)
+    got = trk.propagate_points(feats.cuda(), [(0, pts)], (h, w))[0].cpu().numpy()
+    err = np.abs(got - want).max(axis=-1)
+    assert float((err <= 0.5).mean()) >= 0.95, err
+    assert float(np.median(err)) < 1e-2
+
+
+def test_hr_vos_entry_matches_oracle_loop():
+    """``forward_test_vos`` = forward_test_backward_save_mem(imgs, ref_seg_map, img_meta) (vanilla_tracker.py:663-831):
+    nearest-resized one-hot labels, local-window propagation, decode -- against the oracle loop on the same features."""
+    import fgvc_b200
+    torch.manual_seed(0)
+    cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=10, with_first=True)
+    trk = fgvc_b200.HRVanillaTracker(stride=2, backbone=dict(type="ResNet", depth=18, strides=(1, 1, 1, 4),
+                                                             out_indices=(2,), pool_type="none"), test_cfg=cfg).cuda().eval()
+    from fgvc_b200 import synthetic as S
+    T, h, w = 5, 48, 64
+    frames = S.synthetic_video(T, h, w, seed=4)                       # [T,3,h,w]
+    imgs = frames.transpose(0, 1)[None, None]                          # [1,1,3,T,h,w]
+    seg = S.voronoi_mask(h, w, 4, seed=2)
+    out = trk.forward_test_vos(imgs, seg[None], [dict(original_shape=(h, w, 3))])
+    assert len(out) == 1 and out[0].shape == (T, h, w)
+    feats = trk.get_feats(frames.cuda()).cpu()
+    _, want = O.track_masks_hr_port(feats, seg, (h, w), cfg)
+    agree = (torch.from_numpy(out[0].astype(np.int64)) == want).float().mean(dim=(1, 2))
+    assert float(agree.min()) >= 0.995, agree
+    assert bool((torch.from_numpy(out[0][0].astype(np.int64)) == seg).all())
+    # a padded clip with another original size goes through the reference's resize chain: shape and frame 0 only
+    out2 = trk.forward_test_vos(imgs[..., :47, :63], seg[None, :47, :63], [dict(original_shape=(60, 80, 3))])
+    assert out2[0].shape == (T, 60, 80)

@@ -178,3 +178,31 @@ def test_c2f_clip_loop_port_matches_genuine_operator_loop(golden_dir):
                                        torch.from_numpy(d["points"]), tuple(int(x) for x in d["image_hw"]), cfg)
     assert (torch.stack(outs) - torch.from_numpy(d["outs"])).abs().max() < 2e-6
     assert np.abs(traj - d["traj"]).max() < 1e-3
+
+
+def test_nearest_resize_restatement_matches_pillow():
+    """pil_nearest_interpolate (common/utils.py:39-56) goes through PIL's NEAREST: the oracle's index formula and the
+    product's device version must pick the same source pixels as Pillow itself."""
+    from PIL import Image
+    from fgvc_b200.tracker import nearest_resize
+    rs = np.random.RandomState(0)
+    for (H, W, h, w) in [(48, 86, 24, 43), (37, 53, 18, 26), (20, 20, 7, 9), (480, 854, 240, 427), (9, 7, 9, 7)]:
+        seg = rs.randint(0, 6, (H, W)).astype(np.uint8)
+        want = np.asarray(Image.fromarray(seg).resize((w, h), Image.NEAREST))
+        got = O.nearest_resize_port(torch.from_numpy(seg), (h, w)).numpy()
+        assert (got == want).all(), (H, W, h, w)
+        assert (nearest_resize(torch.from_numpy(seg), (h, w)).numpy() == want).all()
+
+
+def test_correlation_unfold_restatement_is_the_windowed_dot_product():
+    """oracle.correlation_unfold (the F.unfold restatement of mmcv.ops.Correlation, parity unpinned for that op)
+    against an explicit loop over displacements: <q[y,x], k[y+dy,x+dx]>, zero outside the image, (dy, dx) row-major."""
+    g = torch.Generator().manual_seed(2)
+    q, k = torch.randn(2, 5, 6, 7, generator=g), torch.randn(2, 5, 6, 7, generator=g)
+    r = 2
+    got = O.correlation_unfold(q, k, r)
+    kp = torch.nn.functional.pad(k, (r, r, r, r))
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            want = (q * kp[:, :, r + dy:r + dy + 6, r + dx:r + dx + 7]).sum(1)
+            assert (got[:, (dy + r) * (2 * r + 1) + dx + r] - want).abs().max() < 1e-5

@@ -3,8 +3,8 @@
 
 The reference defines the operator but no driver: its output lives on the COARSE query
 grid while its memory labels are consumed at FINE resolution.  This module closes the loop in the simplest way the
-reference's own tracker suggests (vanilla_tracker.py:305-412) and ``oracle/oracle.py::track_clip_c2f_port`` mirrors
-it step by step around the genuine / restated operator:
+reference's own tracker suggests (vanilla_tracker.py:305-412); the test harness restates the same loop step by step
+around the genuine operator (tests/golden/c2f_driver.npz):
 
     S_fine[0]  = gaussian heat-maps of the query points at the fine stride          (vanilla_tracker.py:204-221)
     for t = 1 .. T-1:

@@ -56,7 +56,8 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) inv[pp] = normalize ? fmaxf(sqrtf(acc), 1e-12f) : 1.f;
+    // one reciprocal per pixel (x * (1 / max(|x|, eps)) is within 1 ulp of F.normalize's x / max(|x|, eps))
+    if (lane == 0) inv[pp] = normalize ? __frcp_rn(fmaxf(sqrtf(acc), 1e-12f)) : 1.f;
   }
   __syncthreads();
   const int64_t slot_off = (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
@@ -66,8 +67,8 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
     const int pp = i / c2n, c = 2 * (i - pp * c2n);
     const int p = p0 + pp;
     if (p < n_pix) {
-      const float x0 = __fdiv_rn(tile[c * 33 + pp], inv[pp]);
-      const float x1 = __fdiv_rn(tile[(c + 1) * 33 + pp], inv[pp]);
+      const float x0 = tile[c * 33 + pp] * inv[pp];
+      const float x1 = tile[(c + 1) * 33 + pp] * inv[pp];
       if (FMT == FGVC_BANK_TF32) {
         float* hi = reinterpret_cast<float*>(bank_v) + slot_off;
         float* lo = hi + (int64_t)n_pix * C;

@@ -195,6 +195,54 @@ def gen_tapvid_metrics():
     np.savez_compressed(os.path.join(OUT, "tapvid_metrics.npz"), **d)
 
 
+def gen_eval_metrics():
+    """DAVIS J & F, JHMDB PCK and the TAP-Vid query packaging from the genuine functions."""
+    rs = np.random.RandomState(21)
+    m = ref_loader.load_davis_metrics()
+    T, H, W = 9, 48, 64
+    gt, res = np.zeros((3, T, H, W), bool), np.zeros((2, T, H, W), bool)          # the 3rd object has no result
+    for o in range(3):
+        for t in range(T):
+            y, x = 5 + 2 * t + 7 * o, 6 + 3 * t + 2 * o
+            gt[o, t, y:y + 12, x:x + 16] = True
+            if o < 2:
+                d = t // 2                                                        # the result drifts: decay > 0
+                res[o, t, y + d:y + 12 + d, x - d:x + 16 - d + o] = True
+    res[1, 4] = False                                                             # an empty prediction
+    out = m.JFM(gt.copy(), res.copy(), 3)
+    d = dict(jf_gt=gt, jf_res=res)
+    for k, v in out.items():
+        d[f"jf_{k}"] = np.asarray(v, dtype=np.float64)
+    d["jf_iou_obj0"] = m.db_eval_iou(gt[0].copy(), res[0].copy())
+    d["jf_f_obj0"] = m.db_eval_boundary(gt[0].copy(), res[0].copy())
+    cp, dist = ref_loader.load_jhmdb_pck()
+    P, Tp = 15, 11
+    gtp = rs.rand(2, P, Tp) * 200 + 20
+    pred = gtp + rs.randn(2, P, Tp) * rs.choice([2.0, 10.0, 40.0], (1, P, Tp))
+    pred[0, 3, 2] = -1                                                            # an invisible prediction
+    pred[:, 7, :] = -1
+    pred[:, 7, 5] = gtp[:, 7, 5] + 1.0
+    dd = dist(pred.copy(), gtp.copy(), P)
+    d.update(pck_pred=pred, pck_gt=gtp, pck_dist=np.array([np.asarray(a).ravel().sum() for a in dd]),
+             pck_count=np.array([np.asarray(a).size for a in dd]),
+             pck_values=np.array([np.mean(cp(dd, a)) for a in (0.1, 0.2, 0.3, 0.4, 0.5)]))
+    first, strided = ref_loader.load_tapvid_query_samplers()
+    N, Tq, h, w = 7, 12, 16, 20
+    occ = rs.rand(N, Tq) < 0.4
+    occ[2] = True                                                                 # a track that is never visible
+    pts = rs.rand(N, Tq, 2)
+    video = rs.randint(0, 256, (Tq, h, w, 3)).astype(np.uint8)
+    frames = video.astype(np.float32) / 255.0 * 2 - 1
+    pix = pts * np.array([w, h])
+    a, b = first(occ.copy(), pix.copy(), frames), strided(occ.copy(), pix.copy(), frames, query_stride=5)
+    d.update(tv_video=video, tv_points=pts, tv_occluded=occ, tv_hw=np.array([h, w]))
+    for tag, r in (("first", a), ("strided", b)):
+        d[f"tv_{tag}_query_points"] = r["query_points"]
+        d[f"tv_{tag}_target_points"] = r["target_points"]
+        d[f"tv_{tag}_occluded"] = r["occluded"]
+    np.savez_compressed(os.path.join(OUT, "eval_metrics.npz"), **d)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
@@ -209,6 +257,7 @@ def main():
     gen_legacy(ref)
     gen_tracker()
     gen_tapvid_metrics()
+    gen_eval_metrics()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

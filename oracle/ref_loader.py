@@ -284,3 +284,70 @@ def load_tapvid_metrics():
     ns = dict(np=np, Iterable=Iterable, Mapping=Mapping)
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
     return ns["compute_tapvid_metrics"]
+
+
+def load_davis_metrics():
+    """Genuine DAVIS J & F functions (mmpt/core/evaluation/metrics.py).  The file imports cv2 (present) and mmcv
+    (stand-in) and uses numpy aliases / skimage.morphology.disk that this container lacks: ``np.bool`` is re-created
+    and a two-line ``disk`` (pixels with dy^2 + dx^2 <= r^2, skimage's definition) is provided as skimage.morphology."""
+    import types
+    import numpy as np
+    if not hasattr(np, "bool"):
+        np.bool = bool
+    _install_mmcv_standin()
+    if "skimage" not in sys.modules:
+        sk, mo = types.ModuleType("skimage"), types.ModuleType("skimage.morphology")
+
+        def disk(radius):
+            r = int(radius)
+            y, x = np.mgrid[-r:r + 1, -r:r + 1]
+            return (y * y + x * x <= r * r).astype(np.uint8)
+        mo.disk = disk
+        sk.morphology = mo
+        sys.modules["skimage"], sys.modules["skimage.morphology"] = sk, mo
+    return _load("mmpt_ref_davis_metrics", "mmpt/core/evaluation/metrics.py")
+
+
+def load_jhmdb_pck():
+    """Genuine ``JhmdbVideoDataset.compute_pck`` and the distance loop of ``pck_evaluate``
+    (mmpt/datasets/jhmdb_dataset.py:143-233), taken by ast (the class needs the dataset registry): returns
+    (compute_pck, distances(pred_poses, gt_poses, n_keypoints) -> list of per-joint arrays)."""
+    import ast
+    import numpy as np
+    path = os.path.join(REF_ROOT, "mmpt/datasets/jhmdb_dataset.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef)][0]
+    fns = {n.name: n for n in cls.body if isinstance(n, ast.FunctionDef)}
+    cp = fns["compute_pck"]
+    cp.decorator_list = []
+    ns = dict(np=np)
+    exec(compile(ast.Module(body=[cp], type_ignores=[]), path, "exec"), ns)
+    # the per-video distance loop: lines of pck_evaluate between 'joint_visible =' and the end of the double loop
+    lines = src.splitlines()
+    start = next(i for i, l in enumerate(lines) if "joint_visible = pred_poses[0] > 0" in l)
+    end = next(i for i, l in enumerate(lines) if "dist_all[t] = np.append(dist_all[t], [[dist]])" in l)
+    body = "\n".join(l[12:] for l in lines[start:end + 1])
+
+    def distances(pred_poses, gt_poses, n_keypoints):
+        class _S:
+            NUM_KEYPOINTS = n_keypoints
+        env = dict(np=np, self=_S, pred_poses=pred_poses, gt_poses=gt_poses, clip_len=gt_poses.shape[-1],
+                   dist_all=[np.zeros((0, 0)) for _ in range(n_keypoints)])
+        exec(body, env)
+        return env["dist_all"]
+    return ns["compute_pck"], distances
+
+
+def load_tapvid_query_samplers():
+    """Genuine ``sample_queries_first`` / ``sample_queries_strided`` (tapvid_evaluation_datasets.py:297-401), by ast."""
+    import ast
+    from typing import Iterable, Mapping, Optional
+    import numpy as np
+    path = os.path.join(REF_ROOT, "mmpt/datasets/tapvid_evaluation_datasets.py")
+    tree = ast.parse(open(path).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("sample_queries_first",
+                                                                               "sample_queries_strided")]
+    ns = dict(np=np, Iterable=Iterable, Mapping=Mapping, Optional=Optional)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    return ns["sample_queries_first"], ns["sample_queries_strided"]

@@ -206,3 +206,27 @@ def test_correlation_unfold_restatement_is_the_windowed_dot_product():
         for dx in range(-r, r + 1):
             want = (q * kp[:, :, r + dy:r + dy + 6, r + dx:r + dx + 7]).sum(1)
             assert (got[:, (dy + r) * (2 * r + 1) + dx + r] - want).abs().max() < 1e-5
+
+
+def test_davis_jf_pck_and_tapvid_packaging_match_the_genuine_functions(golden_dir):
+    """fgvc_b200.metrics (device-side J & F, PCK, TAP-Vid record packaging) against outputs of the genuine
+    mmpt functions (metrics.py:11-256, jhmdb_dataset.py:143-233, tapvid_evaluation_datasets.py:297-401)."""
+    from fgvc_b200 import metrics as M
+    d = np.load(os.path.join(golden_dir, "eval_metrics.npz"))
+    got = M.jfm(d["jf_gt"], d["jf_res"])
+    for k in ("JM", "JR", "JD", "FM", "FR", "FD"):
+        assert np.allclose(np.asarray(got[k]), d[f"jf_{k}"], atol=1e-12, equal_nan=True), k
+    assert np.allclose(M.db_eval_iou(d["jf_gt"][0], d["jf_res"][0]).numpy(), d["jf_iou_obj0"], atol=1e-12)
+    assert np.allclose(M.db_eval_boundary(d["jf_gt"][0], d["jf_res"][0]).numpy(), d["jf_f_obj0"], atol=1e-12)
+    dist = M.pck_distances(d["pck_pred"], d["pck_gt"])
+    assert [x.numel() for x in dist] == d["pck_count"].tolist()
+    assert np.allclose([float(x.sum()) for x in dist], d["pck_dist"], atol=1e-9)
+    assert np.allclose(list(M.pck(dist).values()), d["pck_values"], atol=1e-9)
+    h, w = (int(x) for x in d["tv_hw"])
+    for mode in ("first", "strided"):
+        s = M.tapvid_sample(dict(video=d["tv_video"], points=d["tv_points"], occluded=d["tv_occluded"]), (h, w), mode)
+        q = d[f"tv_{mode}_query_points"]                               # [1,n,3] (t, y, x)
+        assert np.allclose(s["query_points"].numpy(), q[:, :, [0, 2, 1]], atol=1e-5)
+        assert np.allclose(s["trajectories"].numpy(), np.transpose(d[f"tv_{mode}_target_points"], (0, 2, 1, 3)), atol=1e-4)
+        assert (s["visibilities"].numpy() == ~np.transpose(d[f"tv_{mode}_occluded"], (0, 2, 1))).all()
+        assert s["rgbs"].shape == (1, d["tv_video"].shape[0], 3, h, w) and float(s["rgbs"].abs().max()) <= 1.0

@@ -86,6 +86,41 @@ class VanillaTracker(nn.Module):
             outs.append(f.float())
         return torch.cat(outs, dim=0)
 
+    @torch.no_grad()
+    def encode_to_bank(self, frames):
+        """frames [T,3,h,w] -> FeatureBank of the clip, encoder and K0 overlapped: the (PyTorch) encoder runs on the
+        current stream in chunks of ``batch_step`` frames (vanilla_tracker.py:133-153), and K0 (normalise + split +
+        pixel-major) of chunk i runs on a side stream while the encoder works on chunk i + 1.  Features go straight
+        into the bank: the [T,C,Hf,Wf] fp32 tensor of the whole clip (the reference moves it to the host and back)
+        is never assembled.  ``test_cfg.encoder_channels_last`` runs the encoder in channels-last memory format."""
+        cfg = self.test_cfg
+        step = cfg.get("batch_step", 5)
+        T = frames.shape[0]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_k0_stream", None) is None:
+            self._k0_stream = torch.cuda.Stream(device=frames.device)
+        side = self._k0_stream
+        side.wait_stream(cur)
+        bank = None
+        for s0 in range(0, T, step):
+            x = frames[s0:s0 + step]
+            if cfg.get("encoder_channels_last", False):
+                x = x.contiguous(memory_format=torch.channels_last)
+            f = self.extract_feat(x)
+            if isinstance(f, (tuple, list)):
+                f = f[0]
+            f = f.float().contiguous()
+            if bank is None:
+                bank = FeatureBank(T, f.shape[1], f.shape[2], f.shape[3], frames.device, split=cfg.get("split"))
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                bank.load_frames(f, s0, normalize=cfg.get("with_norm", cfg.get("withnorm", True)))
+            f.record_stream(side)
+        cur.wait_stream(side)
+        return bank
+
     # --------------------------------------------------------------------- propagation
     two_phase_sharding = True      # apis.sharded_forward_test: forward_test(..., shard=(rank, world))
     local_window = False           # HRVanillaTracker: square window + zero-padded candidates
@@ -98,9 +133,14 @@ class VanillaTracker(nn.Module):
         this rank's frame range only and the top-k lists are all-gathered; the recurrent tail runs for this rank's
         slice of every group's points and the tracks are all-gathered.  Every rank returns the full result."""
         cfg = self.test_cfg
-        T, C, Hf, Wf = feats.shape
+        if isinstance(feats, FeatureBank):               # encode_to_bank: K0 already ran, overlapped with the encoder
+            pre_bank = feats
+            T, C, Hf, Wf, dev = pre_bank.n_slots, pre_bank.C, pre_bank.H, pre_bank.W, pre_bank.buf.device
+        else:
+            pre_bank = None
+            T, C, Hf, Wf = feats.shape
+            dev = feats.device
         h, w = image_hw
-        dev = feats.device
         stride = h // Hf
         precede = cfg.precede_frames
         with_first_mem = cfg.get("with_first", True)
@@ -123,8 +163,11 @@ class VanillaTracker(nn.Module):
                 raise TypeError("the local-window tracker needs neighbor_range")
             # window positions outside the image stay candidates (affinity 0, value 0): merged by the gather
             flags |= _lib.zero_pad_flags(nr // 2, Wf)
-        bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
-        bank.load_frames(feats, 0, normalize=cfg.get("with_norm", cfg.get("withnorm", True)))
+        if pre_bank is not None:
+            bank = pre_bank
+        else:
+            bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
+            bank.load_frames(feats, 0, normalize=cfg.get("with_norm", cfg.get("withnorm", True)))
 
         table = JobTable()
         spans = []   # per group: (first job, t0)
@@ -228,7 +271,7 @@ class VanillaTracker(nn.Module):
         assert rgbs.shape[0] == 1
         B, T = rgbs.shape[:2]
         h, w = rgbs.shape[-2:]
-        feats = self.get_feats(rgbs[0])
+        feats = self.encode_to_bank(rgbs[0])           # FeatureBank: encoder chunks overlapped with K0
         if not self.test_cfg.get("with_first", False):
             traj = self.propagate_points(feats, [(0, query_points[0, :, 1:])], (h, w), shard=shard)[0]
             return trajectories, visibilities, traj[None], torch.zeros_like(visibilities), query_points

@@ -30,6 +30,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Waits are hardware-suspended: mbarrier.try_wait with a time hint parks the thread until the phase flips (it also
 // wakes, spuriously, on other barrier traffic of the CTA), so the retry loop must stay tiny -- it shares the ALU pipe
 // with the warps that have work (profiles/r2_b_epilogue.md: a loop that also read the global timer was 30 % of all

@@ -39,7 +39,7 @@ constexpr int MAX_STAGES = 12;
 constexpr int MAX_NC = 64;                     // keys of a box staged per CTA (x NCTA = N of the MMA)
 constexpr int AHI_COL = 256, ALO_COL = 384;
 constexpr int MAX_ACC = 4;                     // accumulator tiles in TMEM columns [0, 256): 256 / N of them, at most 4
-constexpr int EPI_WG = 4;                     // epilogue warpgroups: 4 warps per TMEM lane quarter share the rows of a box
+constexpr int EPI_WG = 2;                     // epilogue warpgroups: 4 warps per TMEM lane quarter share the rows of a box
 constexpr int THREADS = 64 + 128 * EPI_WG;
 constexpr int MAX_BOXES = 3840;                // per box list (masked halo / whole frame)
 constexpr int THR_BYTES = 128 * EPI_WG * 4;    // running K-th values of the partial lists, shared per query
@@ -540,9 +540,99 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     // 7.09 ms on the bench clip, but made tied results vary from run to run: profiles/r2_b_epilogue.md.)
     const int hw_n = WIN ? p.rf : p.reach;                 // halfw[0 .. hw_n], halfw[hw_n + 1] = -1
     const uint32_t lane_base = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(wg * 16);
+    int n_total = 0;                                       // boxes of this CTA
+    for (int e = e_lo; e < e_hi; ++e) n_total += nbox[(!WIN && (p.ent[e] & FGVC_MEM_UNMASKED)) ? 1 : 0];
     auto run = [&](auto rows_c) {
       constexpr int ROWS = decltype(rows_c)::value;        // key rows of a box per thread
       uint32_t buf = 0, tpar = 0, seq = 0;                 // accumulator of the next box; bit b = parity of its "full" phase
+      bool in_flight = false;                              // the rows of box `seq` were requested by the previous box
+      // The rows of box i+1 are requested from tensor memory BEFORE box i is scanned (when its accumulator is already
+      // complete), into the other of two register sets: the ~100s of cycles of tcgen05.ld latency and the barrier
+      // round trip then overlap the scan instead of heading every box (profiles/r2_b_epilogue.md: long-scoreboard
+      // and fixed-latency waits dominated the epilogue's stalls at ~4.5 warps per scheduler).
+      constexpr bool PREFETCH = ROWS <= 2;                 // (4 rows x 2 sets would not fit the register budget)
+      uint32_t ra[ROWS][16], rb[PREFETCH ? ROWS : 1][16];
+      auto issue_rows = [&](uint32_t b_, uint32_t (&r)[ROWS][16]) {
+        const uint32_t taddr = lane_base + b_ * acc_cols;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) tmem_ld16_issue(taddr + 16 * EPI_WG * rr, r[rr]);
+      };
+      (void)issue_rows;
+      auto box = [&](uint32_t (&rc)[ROWS][16], uint32_t (&rn)[PREFETCH ? ROWS : 1][16], int e, int by, int bx,
+                     bool masked, bool mine, int pos_base, int cy, int cx) {
+        // 16-bit interval masks of the in-mask, in-image keys of this thread's key rows: the half width at
+        // |ky - cy| comes from the table (-1 = row out of reach; unmasked entries: the whole row)
+        uint32_t bits[ROWS];
+        bool hot[ROWS];
+        const bool dump = !WIN && p.dbg != nullptr && (int)seq < p.dbg_max_boxes;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+          const int row = wg + EPI_WG * rr;
+          const int ky = by + row;
+          int hw = p.W;
+          if (masked) hw = halfw[min(abs(ky - cy), hw_n + 1)];
+          const int lo = max(max(cx - hw, 0) - bx, 0);
+          const int hi = min(min(cx + hw, p.W - 1) - bx, 15);
+          const bool ok = row < p.BH;
+          bits[rr] = (ok && mine && hw >= 0 && hi >= lo && ky < p.H) ? ((2u << hi) - (1u << lo)) : 0u;
+          hot[rr] = ok && (__any_sync(0xffffffffu, bits[rr] != 0) || dump) && !(p.exp_flags & 2);   // warp-uniform
+        }
+        if (!in_flight) {
+          mbar_wait_sleep(tfull_bar + buf, (tpar >> buf) & 1u);
+          tc_fence_after();
+          issue_rows(buf, rc);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) reg_fence16(rc[rr]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                   // accumulator is in registers: hand the tile back
+          if (NCTA == 2) mbar_arrive_cluster(tempty_leader + 8u * buf); else mbar_arrive(tempty_bar + buf);
+        }
+        if (dump) {
+#pragma unroll
+          for (int rr = 0; rr < ROWS; ++rr) {
+            if (!hot[rr]) continue;
+            const int row = wg + EPI_WG * rr;
+            float* d = p.dbg + ((int64_t)seq * 128 + m) * 128 + row * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = __uint_as_float(rc[rr][j]) * FGVC_F16_ACC_INV;
+            if (p.dbg_meta != nullptr && m == 0 && row == 0) {
+              p.dbg_meta[4 * seq + 0] = e; p.dbg_meta[4 * seq + 1] = by;
+              p.dbg_meta[4 * seq + 2] = bx; p.dbg_meta[4 * seq + 3] = N;
+            }
+          }
+        }
+        tpar ^= 1u << buf;
+        buf = (buf + 1 == (uint32_t)n_acc) ? 0u : buf + 1;
+        ++seq;
+        // request the next box's rows now if its accumulator is already complete (non-blocking probe)
+        in_flight = false;
+        if constexpr (PREFETCH) {
+          if ((int)seq < n_total && mbar_test_wait(tfull_bar + buf, (tpar >> buf) & 1u)) {
+            tc_fence_after();
+            issue_rows(buf, rn);
+            in_flight = true;
+          }
+        }
+        if (p.exp_flags & 1) return;
+        // The K-th value of ANY partial list of this query bounds the final K-th value from below, so no list
+        // needs candidates under the largest of them: the warpgroups publish theirs when it changes (a stale value
+        // is only a weaker bound).  Without this each of the lists climbs to the final threshold on its own.
+        float floor_ = -INFINITY;
+        if (!(p.exp_flags & 8)) {
+#pragma unroll
+          for (int w2 = 0; w2 < EPI_WG; ++w2) floor_ = fmaxf(floor_, thr_mine[w2 - wg]);
+        }
+        const float thr_before = top.thr();
+        const int kbase = pos_base + (by + wg) * p.W + bx;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr)
+          if (hot[rr]) scan_row<K>(rc[rr], bits[rr], top, kbase + EPI_WG * rr * p.W, floor_, p.exp_flags & 16);
+        if (top.thr() != thr_before) *thr_mine = top.thr();
+      };
+      bool flip = false;
       for (int e = e_hi - 1; e >= e_lo; --e) {           // newest memory frame first: thresholds rise early
         const int raw = p.ent[e];
         const bool masked = WIN || !(raw & FGVC_MEM_UNMASKED);
@@ -568,74 +658,19 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
         for (int b = 0; b < nb; ++b) {
           const uint32_t bb = blist[b];
           const int by = (int)(bb & 0xffffu), bx = (int)(bb >> 16);
-          // 16-bit interval masks of the in-mask, in-image keys of this thread's key rows: the half width at
-          // |ky - cy| comes from the table (-1 = row out of reach; unmasked entries: the whole row)
-          uint32_t bits[ROWS];
-          bool hot[ROWS];
-          const bool dump = !WIN && p.dbg != nullptr && (int)seq < p.dbg_max_boxes;
-#pragma unroll
-          for (int rr = 0; rr < ROWS; ++rr) {
-            const int row = wg + EPI_WG * rr;
-            const int ky = by + row;
-            int hw = p.W;
-            if (masked) hw = halfw[min(abs(ky - cy), hw_n + 1)];
-            const int lo = max(max(cx - hw, 0) - bx, 0);
-            const int hi = min(min(cx + hw, p.W - 1) - bx, 15);
-            const bool ok = row < p.BH;
-            bits[rr] = (ok && mine && hw >= 0 && hi >= lo && ky < p.H) ? ((2u << hi) - (1u << lo)) : 0u;
-            hot[rr] = ok && (__any_sync(0xffffffffu, bits[rr] != 0) || dump) && !(p.exp_flags & 2);   // warp-uniform
+          if constexpr (PREFETCH) {
+            if (flip) box(rb, ra, e, by, bx, masked, mine, pos_base, cy, cx);
+            else box(ra, rb, e, by, bx, masked, mine, pos_base, cy, cx);
+            flip = !flip;
+          } else {
+            box(ra, rb, e, by, bx, masked, mine, pos_base, cy, cx);
           }
-          mbar_wait_sleep(tfull_bar + buf, (tpar >> buf) & 1u);
-          tc_fence_after();
-          uint32_t r[ROWS][16];
-          const uint32_t taddr = lane_base + buf * acc_cols;
-#pragma unroll
-          for (int rr = 0; rr < ROWS; ++rr)
-            if (hot[rr]) tmem_ld16_issue(taddr + 16 * EPI_WG * rr, r[rr]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int rr = 0; rr < ROWS; ++rr) reg_fence16(r[rr]);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {                                 // accumulator is in registers: hand the tile back
-            if (NCTA == 2) mbar_arrive_cluster(tempty_leader + 8u * buf); else mbar_arrive(tempty_bar + buf);
-          }
-          if (dump) {
-#pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) {
-              if (!hot[rr]) continue;
-              const int row = wg + EPI_WG * rr;
-              float* d = p.dbg + ((int64_t)seq * 128 + m) * 128 + row * 16;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) d[j] = __uint_as_float(r[rr][j]) * FGVC_F16_ACC_INV;
-              if (p.dbg_meta != nullptr && m == 0 && row == 0) {
-                p.dbg_meta[4 * seq + 0] = e; p.dbg_meta[4 * seq + 1] = by;
-                p.dbg_meta[4 * seq + 2] = bx; p.dbg_meta[4 * seq + 3] = N;
-              }
-            }
-          }
-          tpar ^= 1u << buf;
-          buf = (buf + 1 == (uint32_t)n_acc) ? 0u : buf + 1;
-          ++seq;
-          if (p.exp_flags & 1) continue;
-          // The K-th value of ANY partial list of this query bounds the final K-th value from below, so no list
-          // needs candidates under the largest of them: the warpgroups publish theirs when it changes (a stale value
-          // is only a weaker bound).  Without this each of the lists climbs to the final threshold on its own.
-          float floor_ = -INFINITY;
-          if (!(p.exp_flags & 8)) {
-#pragma unroll
-            for (int w2 = 0; w2 < EPI_WG; ++w2) floor_ = fmaxf(floor_, thr_mine[w2 - wg]);
-          }
-          const float thr_before = top.thr();
-          const int kbase = pos_base + (by + wg) * p.W + bx;
-#pragma unroll
-          for (int rr = 0; rr < ROWS; ++rr)
-            if (hot[rr]) scan_row<K>(r[rr], bits[rr], top, kbase + EPI_WG * rr * p.W, floor_, p.exp_flags & 16);
-          if (top.thr() != thr_before) *thr_mine = top.thr();
         }
       }
     };
-    if (p.BH <= EPI_WG) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});
+    if (p.BH <= EPI_WG) run(std::integral_constant<int, 1>{});
+    else if (p.BH <= 2 * EPI_WG) run(std::integral_constant<int, 2>{});
+    else run(std::integral_constant<int, 4>{});
     // ---- merge the partial lists of the warpgroups through the (now idle) ring
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     float* mv = reinterpret_cast<float*>(ring);

@@ -54,6 +54,8 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    if os.environ.get("FGVC_BUILD_DEFS"):          # experiments, e.g. FGVC_BUILD_DEFS=-DFGVC_TC16_STATS
+        flags += os.environ["FGVC_BUILD_DEFS"].split()
     procs = []
     for s in SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))

@@ -402,7 +402,6 @@ def run_ours(args):
                                  # geometry: a query tile multiplies the union of its queries' circles, in whole key
                                  # boxes, for the union of its jobs' memory lists
                                  tile_overhead=overhead, jobs_per_tile=J, aligned=aligned,
-                                 tensor_macs_issued_over_peak=achieved / peak * overhead,
                                  # SURVEY 8d / north_star state the roofline as dense TF32 peak / 3 (3xTF32):
                                  frac_vs_3xtf32_roofline=achieved / (pk["bf16"] / 2.0 / 3.0)),
                    clocks=clocks)

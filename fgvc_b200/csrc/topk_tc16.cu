@@ -10,21 +10,22 @@
 //     D += hi_q * hi_k;   D += hi_q * lo_k;   D += lo_q * hi_k          (D = 256 * affinity, lo*lo < 2^-22 dropped)
 // Both query parts live in tensor memory (2 x C/2 columns, two channels per 32-bit cell), so every MMA is TS-form:
 // an M = 128 (per CTA) tcgen05.mma then costs N/2 cycles, +43 if A came from shared memory
-// (profiles/r1_mma_issue_rates.md).  TMEM: [0,128) accumulator 0, [128,256) accumulator 1, [256,384) hi_q,
-// [384,512) lo_q.
+// (profiles/r1_mma_issue_rates.md).  TMEM: [0,256) up to four accumulator tiles of N columns (the MMA warp may run
+// three boxes ahead of the epilogue), [256,384) hi_q, [384,512) lo_q.
 //
-// Why CTA pairs.  Measured (profiles/r2_a_l2_bound.md): the single-CTA engine moves 64 KB from L2 into shared
-// memory per 1536 tensor cycles and SM -- 7.1 TB/s over the chip, which is the L2 -> SM fabric limit, with the
-// tensor pipe 63 % busy; loading half of every key box made the same launch 21 % faster.  With cta_group::2 a key
-// box serves 256 query rows and each SM of the pair stages only its half of the keys, so the fabric bytes per MAC
-// halve and the tensor pipe becomes the bound.
+// CTA pairs (NCTA = 2) are built and tested but NOT what AUTO runs: a cta_group::2 MMA costs the same N/2 cycles
+// per SM as a single-CTA one (profiles/r2_mma_pair_rates.md), a 256-row tile has the larger halo (+17 % tensor
+// work on the bench clip), and the kernel is bound by its epilogue, not by the L2 -> SM fabric
+// (profiles/r2_a_l2_bound.md, profiles/r2_b_epilogue.md).  FGVC_TC16_PAIR=1 selects them.
 //
-// CTA anatomy (576 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane of the
-// pair's leader CTA), warps 2-17 = epilogue: thread = query row (TMEM lane), warpgroup w owns key rows w, w+4 of a
-// box.  A key box is a spatial rectangle (16 x BH pixels of one memory frame): halos are box coordinates and
-// out-of-image pixels are zero-filled by the TMA unit.  The boxes a tile needs are listed once per CTA (centre-out)
-// and walked by all three roles.  The circle / square mask is one 16-bit interval per (thread, key row); candidates
-// above the thread's running K-th value are inserted into a sorted register list in warp-wide rounds.
+// CTA anatomy (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane; of
+// the leader CTA for a pair), warps 2-9 = epilogue: thread = query row (TMEM lane), warpgroup w owns key rows
+// w, w + 2 (, ...) of a box.  A key box is a spatial rectangle (16 x BH pixels of one memory frame): halos are box
+// coordinates and out-of-image pixels are zero-filled by the TMA unit.  The boxes a tile needs are listed once per
+// CTA (centre-out) and walked by all three roles.  The circle / square mask is one 16-bit interval per (thread, key
+// row); a row whose maximum is below the floor of every lane is rejected by one vote, candidates above the thread's
+// running K-th value are inserted into a sorted register list in warp-wide rounds; the partial lists of a query
+// (one per warpgroup) share their K-th values through shared memory.
 #include <stdlib.h>
 
 #include <type_traits>

@@ -121,7 +121,7 @@ FGVC_API int fgvc_device_count(void);
 /* kernels launched by this library in this process so far (bench.py's gpu_launches) */
 FGVC_API int64_t fgvc_launch_count(void);
 
-/* K0 -- F.normalize(dim=C) + NCHW -> pixel-major + TF32 hi/lo split
+/* K0 -- F.normalize(dim=C) + NCHW -> pixel-major + hi/lo split in the bank's format (see fgvc_bank_format)
  * (local_attention.py:308-310).  src: n_frames frames of [C][H*W], consecutive frames
  * src_frame_stride floats apart, channels src_chan_stride floats apart (so a
  * [1,C,T,H,W] key stack can be read in place).  Writes bank slots
@@ -170,8 +170,9 @@ FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int3
  * job).  A tile group covers the memory entries [u_begin, u_end) of the union tables, cut into `split` contiguous
  * parts (one CTA or CTA pair each); part y writes list  out_group * split + y  of its jobs, so `groups` must be
  * split x (number of distinct out_group values) and every (job, list) must be written by exactly one tile group.
- * jobs_per_tile in {1, 2, 4}: tile rows = jobs_per_tile jobs x a pixel block.  On large maps a tile is a CTA PAIR
- * (256 rows, tcgen05 cta_group::2: both SMs of the pair multiply the same key box and each stages half of it).
+ * jobs_per_tile in {1, 2, 4}: tile rows = jobs_per_tile jobs x a pixel block.  A tile is one CTA (128 rows); with the
+ * environment variable FGVC_TC16_PAIR=1 and a map large enough it is a CTA PAIR (256 rows, tcgen05 cta_group::2: both
+ * SMs of the pair multiply the same key box and each stages half of it) -- same results, not faster.
  * fgvc_packed_tile_shape reports the pixel block of one job, the key-box height and the CTAs per tile the launcher
  * will use (for costing). */
 FGVC_API int fgvc_affinity_topk_packed(const void* feat_bank, int32_t n_slots, int32_t H, int32_t W, int32_t C,

@@ -162,68 +162,59 @@ __device__ __forceinline__ void cell_range(int i0, int in_size, int out_size, fl
 
 // Soft-argmax of the bilinearly up-sampled map WITHOUT evaluating every output pixel.  An up-sampled
 // value is a convex combination of its 4 taps, so it cannot exceed their maximum:
-//   1. seed: the 5 largest SOURCE pixels; evaluate the output pixels around them; tau = the topk-th
-//      best up-sampled value found (a lower bound of the final topk-th value);
-//   2. scan the source cells; only cells whose largest tap reaches tau (minus a rounding margin) can
-//      hold a winner -- evaluate just those.
+//   1. seed: the largest SOURCE pixel (found while the map is staged in shared memory); one warp evaluates the
+//      output pixels around it; tau = the topk-th best up-sampled value found there -- `topk` distinct outputs
+//      reach it, so it is a lower bound of the final topk-th value, whatever set of outputs was looked at;
+//   2. scan the source cells; only cells whose largest tap reaches tau (minus a rounding margin) can hold a
+//      winner -- evaluate just those (each output belongs to exactly one cell, so none is seen twice).
 // Peaked heat-maps touch a handful of cells; a flat map degrades to the full evaluation.  Exact.
 // Zero test: labels are non-negative (convex combinations of gaussians / one-hots), for which
 // "sum of the up-sampled map == 0" <=> "every source value is 0".
-__device__ void soft_argmax_pruned(const float* m, int H, int W, int out_h, int out_w, int topk, float* out_xy) {
-  __shared__ float win_v[CK];
-  __shared__ int win_i[CK];
-  __shared__ int any_nz[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const BilinearSrc src{m, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
-  // ---- 1. seeds
-  TopK<CK> top;
-  top.init();
-  bool nz = false;
-  for (int i = tid; i < H * W; i += 256) {
-    const float v = m[i];
-    nz |= v != 0.f;
-    push_key(top, v, i);
-  }
-  nz = __any_sync(0xffffffffu, nz);
-  if (lane == 0) any_nz[warp] = nz;
-  block_topk(top, topk, win_v, win_i);
-  bool nonzero = false;
-  for (int w = 0; w < 8; ++w) nonzero |= any_nz[w] != 0;
-  // rectangles of output pixels around the seeds (the outputs whose taps include the seed pixel)
-  int ry0[CK], ry1[CK], rx0[CK], rx1[CK];
+// ONE WARP PER MAP, no block barriers: the map is streamed from global memory once (16-byte loads: arg-max, zero
+// test, and the maximum of each of a lane's <= 32 load slots, kept in shared memory); step 2 re-reads only the
+// slots whose maximum reaches tau.  8 maps per CTA progress independently, so the serial part of one map (seed
+// rectangle, selections) hides behind the others.
+// (The first version -- one CTA per map staged in shared memory, 5 seeds, three block-wide selections, the seeds'
+// output ranges searched by every thread, a division per cell -- took 11 k instructions per thread and 35 ms for
+// the 255 k maps of a 250-frame, 1024-point clip; this one takes ~3 ms, the time to read the maps.)
+
+// warp-wide selection of the `topk` best pairs from the lanes' sorted lists -> win_v / win_i (lane 0 writes)
+__device__ __forceinline__ void warp_topk(const TopK<CK>& top, int topk, float* win_v, int* win_i) {
+  const int lane = threadIdx.x & 31;
+  int head = 0;
   for (int r = 0; r < topk; ++r) {
-    const int sd = win_i[r];
-    if (sd < 0) { ry0[r] = 1; ry1[r] = 0; rx0[r] = 1; rx1[r] = 0; continue; }
-    const int sy = sd / W, sx = sd - sy * W;
-    int t0, t1;
-    cell_range(max(sy - 1, 0), H, out_h, src.sy, &ry0[r], &t0);
-    cell_range(sy, H, out_h, src.sy, &t1, &ry1[r]);
-    cell_range(max(sx - 1, 0), W, out_w, src.sx, &rx0[r], &t0);
-    cell_range(sx, W, out_w, src.sx, &t1, &rx1[r]);
-  }
-  __syncthreads();
-  top.init();
-  for (int r = 0; r < topk; ++r) {
-    const int nx = rx1[r] - rx0[r] + 1, n = max(0, ry1[r] - ry0[r] + 1) * max(0, nx);
-    for (int i = tid; i < n; i += 256) {
-      const int oy = ry0[r] + i / nx, ox = rx0[r] + i % nx;
-      bool seen = false;                        // already covered by an earlier seed's rectangle
-      for (int q = 0; q < r; ++q) seen |= oy >= ry0[q] && oy <= ry1[q] && ox >= rx0[q] && ox <= rx1[q];
-      if (!seen) push_key(top, src.at(oy, ox), oy * out_w + ox);
+    float v = -INFINITY;
+    int i = -1;
+#pragma unroll
+    for (int j = 0; j < CK; ++j)
+      if (j == head) { v = top.v[j]; i = top.id[j]; }
+    int t = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, t, o);
+      if (key_gt(ov, oi, v, i)) { v = ov; i = oi; t = ot; }
     }
+    if (lane == t) ++head;
+    if (lane == 0) { win_v[r] = v; win_i[r] = i; }
   }
-  block_topk(top, topk, win_v, win_i);
-  // tau = the topk-th best of these (distinct) output pixels: a lower bound of the final topk-th value
-  float tau = (win_i[topk - 1] >= 0) ? win_v[topk - 1] : -INFINITY;
-  __syncthreads();
-  const float tau_safe = tau == -INFINITY ? -INFINITY : tau - fabsf(tau) * 4e-6f - 1e-30f;
-  // ---- 2. cells that can hold a winner
-  top.init();
-  for (int c = tid; c < H * W; c += 256) {
-    const int i0 = c / W, j0 = c - i0 * W;
-    const int i1 = min(i0 + 1, H - 1), j1 = min(j0 + 1, W - 1);
-    const float mx = fmaxf(fmaxf(m[i0 * W + j0], m[i0 * W + j1]), fmaxf(m[i1 * W + j0], m[i1 * W + j1]));
-    if (!(mx >= tau_safe)) continue;
+  __syncwarp();
+}
+
+// step 2 for one hot pixel: evaluate the cells it is a tap of (each cell from its first hot tap only)
+__device__ __forceinline__ void visit_hot_pixel(const BilinearSrc& src, int i, float tau_safe, int out_h, int out_w,
+                                                TopK<CK>& top) {
+  const float* m = src.m;
+  const int H = src.H, W = src.W;
+  const int pi = i / W, pj = i - pi * W;
+  for (int d = 0; d < 4; ++d) {
+    const int di = d >> 1, dj = d & 1;
+    const int i0 = pi - di, j0 = pj - dj;
+    if (i0 < 0 || j0 < 0) continue;
+    bool earlier = false;                      // an earlier tap (i0 + ei, j0 + ej), (ei, ej) < (di, dj), is hot too
+    for (int e = 0; e < d; ++e) earlier |= __ldg(m + (i0 + (e >> 1)) * W + min(j0 + (e & 1), W - 1)) >= tau_safe;
+    if (earlier) continue;
     int y0, y1, x0, x1;
     cell_range(i0, H, out_h, src.sy, &y0, &y1);
     cell_range(j0, W, out_w, src.sx, &x0, &x1);
@@ -231,21 +222,121 @@ __device__ void soft_argmax_pruned(const float* m, int H, int W, int out_h, int 
     for (int oy = y0; oy <= y1; ++oy)
       for (int ox = x0; ox <= x1; ++ox) push_key(top, src.at(oy, ox), oy * out_w + ox);
   }
-  block_topk(top, topk, win_v, win_i);
-  if (tid == 0) write_coords(win_v, win_i, topk, out_w, nonzero, out_xy);
 }
 
-__global__ void __launch_bounds__(256)
-heatmap_coords_kernel(const float* __restrict__ maps, int H, int W, int out_h, int out_w, int topk,
-                      int use_smem, float* __restrict__ out_xy) {
-  extern __shared__ float smap[];
-  const float* m = maps + (int64_t)blockIdx.x * H * W;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < H * W; i += 256) smap[i] = __ldg(m + i);
-    __syncthreads();
-    m = smap;
+constexpr int MAPS_PER_CTA = 8;
+constexpr int SLOTS = 32;          // per-lane slot maxima kept in shared memory (4 KB per map)
+
+__global__ void __launch_bounds__(32 * MAPS_PER_CTA)
+heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, int out_h, int out_w, int topk,
+                      float* __restrict__ out_xy) {
+  __shared__ float win_v_s[MAPS_PER_CTA][CK];
+  __shared__ int win_i_s[MAPS_PER_CTA][CK];
+  __shared__ float slot_max_s[MAPS_PER_CTA][SLOTS * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int map = blockIdx.x * MAPS_PER_CTA + warp;
+  if (map >= n_maps) return;
+  float* win_v = win_v_s[warp];
+  int* win_i = win_i_s[warp];
+  const float* m = maps + (int64_t)map * H * W;
+  out_xy += 2 * (int64_t)map;
+  const int n = H * W;
+  // ---- 0. stream the map once: arg-max, zero test, and the maximum of every SLOT (a lane's pixels are cut into
+  // <= 32 slots of consecutive loads) kept in shared memory, so that step 2 re-reads only the slots that can
+  // hold a hot pixel
+  float* slot_max = slot_max_s[warp];
+  const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0;
+  const int n_it = vec ? ((n >> 2) + 127) / 128 : (n + 127) / 128;    // iterations of 4 loads per lane
+  const int per_slot = (n_it + SLOTS - 1) / SLOTS;
+  float bv = -INFINITY, mn = INFINITY;
+  int bi = 0;
+  for (int s0 = 0, slot = 0; s0 < n_it; s0 += per_slot, ++slot) {
+    float smx = -INFINITY;
+    for (int it = s0; it < min(s0 + per_slot, n_it); ++it) {
+      if (vec) {
+        const float4* m4 = reinterpret_cast<const float4*>(m);
+        const int n4 = n >> 2;
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(m4 + min(it * 128 + 32 * u + lane, n4 - 1));   // clamped: a repeat
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+          mn = fminf(mn, fminf(fminf(v[u].x, v[u].y), fminf(v[u].z, v[u].w)));
+          smx = fmaxf(smx, mx);
+          if (mx > bv) { bv = mx; bi = min(it * 128 + 32 * u + lane, n4 - 1); }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = min(it * 128 + 32 * u + lane, n - 1);
+          const float v = __ldg(m + i);
+          mn = fminf(mn, v);
+          smx = fmaxf(smx, v);
+          if (v > bv) { bv = v; bi = i; }
+        }
+      }
+    }
+    slot_max[slot * 32 + lane] = smx;
   }
-  soft_argmax_pruned(m, H, W, out_h, out_w, topk, out_xy + 2 * blockIdx.x);
+  if (vec) {                                     // which of the 4 pixels of the best load
+    const float4 v = __ldg(reinterpret_cast<const float4*>(m) + bi);
+    bi = 4 * bi + (v.x == bv ? 0 : (v.y == bv ? 1 : (v.z == bv ? 2 : 3)));
+  }
+  // every value is 0 <=> min == 0 and max == 0
+  if (!__any_sync(0xffffffffu, !(mn == 0.f && bv == 0.f))) {   // np.sum(map) == 0 -> (-1, -1)
+    if (lane == 0) { out_xy[0] = -1.f; out_xy[1] = -1.f; }
+    return;
+  }
+  // the largest source pixel
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv) { bv = ov; bi = oi; }
+  }
+  const BilinearSrc src{m, H, W, (float)H / (float)out_h, (float)W / (float)out_w};
+  // ---- 1. tau from the output pixels around the seed (any distinct outputs give a valid lower bound)
+  TopK<CK> top;
+  top.init();
+  {
+    const int sy = bi / W, sx = bi - sy * W;
+    const int ry = (int)ceilf(1.f / src.sy) + 1, rx = (int)ceilf(1.f / src.sx) + 1;
+    const int cy = (int)(((float)sy + 0.5f) / src.sy), cx = (int)(((float)sx + 0.5f) / src.sx);
+    const int y0 = max(cy - ry, 0), y1 = min(cy + ry, out_h - 1), x0 = max(cx - rx, 0), x1 = min(cx + rx, out_w - 1);
+    const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
+    for (int i = lane; i < cnt; i += 32) {
+      const int oy = y0 + i / nx, ox = x0 + i % nx;
+      push_key(top, src.at(oy, ox), oy * out_w + ox);
+    }
+  }
+  warp_topk(top, topk, win_v, win_i);
+  const float tau = (win_i[topk - 1] >= 0) ? win_v[topk - 1] : -INFINITY;
+  const float tau_safe = tau == -INFINITY ? -INFINITY : tau - fabsf(tau) * 4e-6f - 1e-30f;
+  __syncwarp();
+  // ---- 2. cells that can hold a winner: a cell needs a tap >= tau, i.e. a hot PIXEL; visit the <= 4 cells each
+  // hot pixel is a tap of
+  top.init();
+  for (int s0 = 0, slot = 0; s0 < n_it; s0 += per_slot, ++slot) {
+    if (!(slot_max[slot * 32 + lane] >= tau_safe)) continue;
+    for (int it = s0; it < min(s0 + per_slot, n_it); ++it)
+      for (int u = 0; u < 4; ++u) {
+        if (vec) {
+          const int i4 = it * 128 + 32 * u + lane;
+          if (i4 >= (n >> 2)) continue;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(m) + i4);
+          if (v.x >= tau_safe) visit_hot_pixel(src, 4 * i4, tau_safe, out_h, out_w, top);
+          if (v.y >= tau_safe) visit_hot_pixel(src, 4 * i4 + 1, tau_safe, out_h, out_w, top);
+          if (v.z >= tau_safe) visit_hot_pixel(src, 4 * i4 + 2, tau_safe, out_h, out_w, top);
+          if (v.w >= tau_safe) visit_hot_pixel(src, 4 * i4 + 3, tau_safe, out_h, out_w, top);
+        } else {
+          const int i = it * 128 + 32 * u + lane;
+          if (i < n && __ldg(m + i) >= tau_safe) visit_hot_pixel(src, i, tau_safe, out_h, out_w, top);
+        }
+      }
+  }
+  warp_topk(top, topk, win_v, win_i);
+  if (lane == 0) write_coords(win_v, win_i, topk, out_w, true, out_xy);
 }
 
 __global__ void __launch_bounds__(256)
@@ -488,13 +579,8 @@ extern "C" int fgvc_heatmap_coords(const float* maps, int32_t n_maps, int32_t H,
   FGVC_CHECK_ARG(maps && out_xy && n_maps > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0,
                  "fgvc_heatmap_coords: bad arguments");
   FGVC_CHECK_ARG(topk >= 1 && topk <= CK, "fgvc_heatmap_coords: topk=%d not in [1,%d]", topk, CK);
-  size_t smem = (size_t)H * W * sizeof(float);
-  int use_smem = smem <= 160 * 1024;
-  // per launch: the attribute is per device, and a process may use several
-  if (use_smem && smem > 48 * 1024)
-    FGVC_CUDA(cudaFuncSetAttribute(heatmap_coords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  heatmap_coords_kernel<<<n_maps, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(maps, H, W, out_h, out_w,
-                                                                                     topk, use_smem, out_xy);
+  heatmap_coords_kernel<<<cdiv(n_maps, MAPS_PER_CTA), 32 * MAPS_PER_CTA, 0, (cudaStream_t)stream>>>(
+      maps, n_maps, H, W, out_h, out_w, topk, out_xy);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }

@@ -143,6 +143,34 @@ labels_to_nchw_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __rest
   }
 }
 
+// wide variant (n_pix % 4 == 0): 64 pixels x 64 channels per CTA, 16-byte loads along the channels and 16-byte
+// stores along the pixels
+__global__ void __launch_bounds__(256)
+labels_to_nchw_jobs_wide_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int Lp,
+                                int L, int n_pix, float* __restrict__ maps) {
+  __shared__ float t[64][65];
+  const int slot = jobs[job_begin + blockIdx.z].out_slot;
+  const float* src = lab + (int64_t)slot * n_pix * Lp;
+  float* dst = maps + (int64_t)slot * L * n_pix;
+  const int p0 = blockIdx.x * 64, l0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int j = ty; j < 64; j += 16) {
+    const int p = p0 + j, l = l0 + 4 * tx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < n_pix && l < Lp) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p * Lp + l));
+    t[j][4 * tx] = v.x; t[j][4 * tx + 1] = v.y; t[j][4 * tx + 2] = v.z; t[j][4 * tx + 3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 64; j += 16) {
+    const int l = l0 + j, p = p0 + 4 * tx;
+    if (l < L && p < n_pix)
+      *reinterpret_cast<float4*>(dst + (int64_t)l * n_pix + p) =
+          make_float4(t[4 * tx][j], t[4 * tx + 1][j], t[4 * tx + 2][j], t[4 * tx + 3][j]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gaussian_labels_kernel(const float* __restrict__ pts, int P, int H, int W, int stride, float denom,
                        float* __restrict__ dst, int Lp) {
@@ -215,9 +243,15 @@ int launch_labels_to_nchw_jobs(const float* lab, const fgvc_job* jobs_dev, int j
                                int n_pix, float* maps_nchw, cudaStream_t st) {
   const int n = job_end - job_begin;
   if (n <= 0) return FGVC_OK;
+  const bool wide = n_pix % 4 == 0 && L >= 32 && (reinterpret_cast<uintptr_t>(maps_nchw) & 15) == 0;
   for (int z0 = 0; z0 < n; z0 += 65535) {
-    dim3 grid(cdiv(n_pix, 32), cdiv(L, 32), min(65535, n - z0));
-    labels_to_nchw_jobs_kernel<<<grid, 256, 0, st>>>(lab, jobs_dev, job_begin + z0, Lp, L, n_pix, maps_nchw);
+    if (wide) {
+      dim3 grid(cdiv(n_pix, 64), cdiv(L, 64), min(65535, n - z0));
+      labels_to_nchw_jobs_wide_kernel<<<grid, 256, 0, st>>>(lab, jobs_dev, job_begin + z0, Lp, L, n_pix, maps_nchw);
+    } else {
+      dim3 grid(cdiv(n_pix, 32), cdiv(L, 32), min(65535, n - z0));
+      labels_to_nchw_jobs_kernel<<<grid, 256, 0, st>>>(lab, jobs_dev, job_begin + z0, Lp, L, n_pix, maps_nchw);
+    }
     FGVC_LAUNCH_CHECK();
   }
   return FGVC_OK;

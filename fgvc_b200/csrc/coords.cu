@@ -202,9 +202,16 @@ __device__ __forceinline__ void warp_topk(const TopK<CK>& top, int topk, float* 
   __syncwarp();
 }
 
-// step 2 for one hot pixel: evaluate the cells it is a tap of (each cell from its first hot tap only)
-__device__ __forceinline__ void visit_hot_pixel(const BilinearSrc& src, int i, float tau_safe, int out_h, int out_w,
-                                                TopK<CK>& top) {
+// step 2 for one hot pixel: list the cells it is a tap of (each cell from its first hot tap only) with their output
+// ranges in the warp's shared list; a cell that does not fit is evaluated on the spot
+constexpr int CELL_CAP = 128;
+__device__ __forceinline__ void eval_cell(const BilinearSrc& src, int y0, int y1, int x0, int x1, int out_w,
+                                          TopK<CK>& top) {
+  for (int oy = y0; oy <= y1; ++oy)
+    for (int ox = x0; ox <= x1; ++ox) push_key(top, src.at(oy, ox), oy * out_w + ox);
+}
+__device__ __forceinline__ void list_hot_cells(const BilinearSrc& src, int i, float tau_safe, int out_h, int out_w,
+                                               uint2* cells, int* n_cells, TopK<CK>& top) {
   const float* m = src.m;
   const int H = src.H, W = src.W;
   const int pi = i / W, pj = i - pi * W;
@@ -219,8 +226,9 @@ __device__ __forceinline__ void visit_hot_pixel(const BilinearSrc& src, int i, f
     cell_range(i0, H, out_h, src.sy, &y0, &y1);
     cell_range(j0, W, out_w, src.sx, &x0, &x1);
     if (lerp_coord(y0, src.sy, H).i0 != i0 || lerp_coord(x0, src.sx, W).i0 != j0) continue;   // cell without outputs
-    for (int oy = y0; oy <= y1; ++oy)
-      for (int ox = x0; ox <= x1; ++ox) push_key(top, src.at(oy, ox), oy * out_w + ox);
+    const int slot = (out_h <= 65535 && out_w <= 65535) ? atomicAdd(n_cells, 1) : CELL_CAP;
+    if (slot < CELL_CAP) cells[slot] = make_uint2((uint32_t)y0 | ((uint32_t)y1 << 16), (uint32_t)x0 | ((uint32_t)x1 << 16));
+    else eval_cell(src, y0, y1, x0, x1, out_w, top);
   }
 }
 
@@ -233,6 +241,8 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
   __shared__ float win_v_s[MAPS_PER_CTA][CK];
   __shared__ int win_i_s[MAPS_PER_CTA][CK];
   __shared__ float slot_max_s[MAPS_PER_CTA][SLOTS * 32];
+  __shared__ uint2 cells_s[MAPS_PER_CTA][CELL_CAP];
+  __shared__ int n_cells_s[MAPS_PER_CTA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int map = blockIdx.x * MAPS_PER_CTA + warp;
   if (map >= n_maps) return;
@@ -317,6 +327,10 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
   // ---- 2. cells that can hold a winner: a cell needs a tap >= tau, i.e. a hot PIXEL; visit the <= 4 cells each
   // hot pixel is a tap of
   top.init();
+  uint2* cells = cells_s[warp];
+  int* n_cells = n_cells_s + warp;
+  if (lane == 0) *n_cells = 0;
+  __syncwarp();
   for (int s0 = 0, slot = 0; s0 < n_it; s0 += per_slot, ++slot) {
     if (!(slot_max[slot * 32 + lane] >= tau_safe)) continue;
     for (int it = s0; it < min(s0 + per_slot, n_it); ++it)
@@ -325,15 +339,34 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
           const int i4 = it * 128 + 32 * u + lane;
           if (i4 >= (n >> 2)) continue;
           const float4 v = __ldg(reinterpret_cast<const float4*>(m) + i4);
-          if (v.x >= tau_safe) visit_hot_pixel(src, 4 * i4, tau_safe, out_h, out_w, top);
-          if (v.y >= tau_safe) visit_hot_pixel(src, 4 * i4 + 1, tau_safe, out_h, out_w, top);
-          if (v.z >= tau_safe) visit_hot_pixel(src, 4 * i4 + 2, tau_safe, out_h, out_w, top);
-          if (v.w >= tau_safe) visit_hot_pixel(src, 4 * i4 + 3, tau_safe, out_h, out_w, top);
+          if (v.x >= tau_safe) list_hot_cells(src, 4 * i4, tau_safe, out_h, out_w, cells, n_cells, top);
+          if (v.y >= tau_safe) list_hot_cells(src, 4 * i4 + 1, tau_safe, out_h, out_w, cells, n_cells, top);
+          if (v.z >= tau_safe) list_hot_cells(src, 4 * i4 + 2, tau_safe, out_h, out_w, cells, n_cells, top);
+          if (v.w >= tau_safe) list_hot_cells(src, 4 * i4 + 3, tau_safe, out_h, out_w, cells, n_cells, top);
         } else {
           const int i = it * 128 + 32 * u + lane;
-          if (i < n && __ldg(m + i) >= tau_safe) visit_hot_pixel(src, i, tau_safe, out_h, out_w, top);
+          if (i < n && __ldg(m + i) >= tau_safe) list_hot_cells(src, i, tau_safe, out_h, out_w, cells, n_cells, top);
         }
       }
+  }
+  __syncwarp();
+  // the listed cells, spread over the warp: large cells (strong up-sampling) output by output, small ones cell by cell
+  const int nc = min(*n_cells, CELL_CAP);
+  if (src.sy * src.sx < 1.f / 12.f) {
+    for (int c = 0; c < nc; ++c) {
+      const uint2 r = cells[c];
+      const int y0 = r.x & 0xffff, y1 = r.x >> 16, x0 = r.y & 0xffff, x1 = r.y >> 16;
+      const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
+      for (int k = lane; k < cnt; k += 32) {
+        const int oy = y0 + k / nx, ox = x0 + k % nx;
+        push_key(top, src.at(oy, ox), oy * out_w + ox);
+      }
+    }
+  } else {
+    for (int c = lane; c < nc; c += 32) {
+      const uint2 r = cells[c];
+      eval_cell(src, r.x & 0xffff, r.x >> 16, r.y & 0xffff, r.y >> 16, out_w, top);
+    }
   }
   warp_topk(top, topk, win_v, win_i);
   if (lane == 0) write_coords(win_v, win_i, topk, out_w, true, out_xy);

@@ -10,6 +10,10 @@ import fgvc_b200  # noqa: E402
 from fgvc_b200 import synthetic as S  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg5_tapvid_kinetics"
+if name == "cfg3ii":                     # the coarse-to-fine clip driver
+    import json
+    print(json.dumps(bench.run_c2f_clip(torch.device("cuda", 0), 0, 1)))
+    sys.exit(0)
 c = bench.SECONDARY[name]
 precede = int(sys.argv[2]) if len(sys.argv) > 2 else c["precede"][0]
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 1

@@ -370,10 +370,11 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     const int qy = qy0 + (m >> p.qw_shift), qx = qx0 + (m & (p.QW - 1));
     const bool qvalid = qy < p.HQ && qx < p.WQ;
     int cy_lo = 1 << 30, cy_hi = -1, cx_lo = 1 << 30, cx_hi = -1;
+    int my_cy = 0, my_cx = 0;
     if (qvalid) {
       const int b = max(__ldg(p.best + (int64_t)blockIdx.y * nq_c + qy * p.WQ + qx), 0) % nq_c;
-      cy_lo = cy_hi = (b / p.WQ) * p.scale;
-      cx_lo = cx_hi = (b % p.WQ) * p.scale;
+      my_cy = cy_lo = cy_hi = (b / p.WQ) * p.scale;
+      my_cx = cx_lo = cx_hi = (b % p.WQ) * p.scale;
     }
     cy_lo = __reduce_min_sync(0xffffffffu, cy_lo); cy_hi = __reduce_max_sync(0xffffffffu, cy_hi);
     cx_lo = __reduce_min_sync(0xffffffffu, cx_lo); cx_hi = __reduce_max_sync(0xffffffffu, cx_hi);
@@ -384,23 +385,51 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
       atomicMin(rect + 2, cx_lo); atomicMax(rect + 3, cx_hi);
     }
     asm volatile("bar.sync 2, 128;" ::: "memory");
-    // box list: this CTA's chunk of the boxes of the rectangle grown by rf, clipped to the map (warp 2)
-    if (warp == 2) {
-      int cnt = 0;
-      if (rect[1] >= 0) {                                       // (else: no valid query in the tile)
-        const int y_lo = max(0, rect[0] - p.rf), y_hi = min(p.H - 1, rect[1] + p.rf);
-        const int x_lo = max(0, rect[2] - p.rf), x_hi = min(p.W - 1, rect[3] + p.rf);
-        const int ncols = (x_hi - x_lo) / 16 + 1, nrows = (y_hi - y_lo) / p.BH + 1;
-        const int total = nrows * ncols;
-        const int i_lo = (int)((int64_t)total * blockIdx.z / p.chunks), i_hi = (int)((int64_t)total * (blockIdx.z + 1) / p.chunks);
-        for (int i = i_lo + lane; i < i_hi; i += 32) {
-          const int by = y_lo + (i / ncols) * p.BH, bx = x_lo + (i % ncols) * 16;
-          if (i - i_lo < 2 * MAX_BOXES) boxes[i - i_lo] = (uint32_t)by | ((uint32_t)bx << 16);
-        }
-        cnt = min(i_hi - i_lo, 2 * MAX_BOXES);
+    // The boxes of the rectangle grown by rf, clipped to the map -- minus those no window of the tile touches (a few
+    // far-away arg-max keys stretch the rectangle over most of the frame): every lane marks the boxes of its own
+    // window in a bitmap (scratch: the start of the ring, idle until the producer starts), warp 2 lists this CTA's
+    // chunk of the marked boxes.
+    uint32_t* cover = reinterpret_cast<uint32_t*>(ring);
+    int cnt = 0;
+    if (rect[1] >= 0) {                                         // (else: no valid query in the tile)
+      const int y_lo = max(0, rect[0] - p.rf), y_hi = min(p.H - 1, rect[1] + p.rf);
+      const int x_lo = max(0, rect[2] - p.rf), x_hi = min(p.W - 1, rect[3] + p.rf);
+      const int ncols = (x_hi - x_lo) / 16 + 1, nrows = (y_hi - y_lo) / p.BH + 1;
+      const int total = nrows * ncols, words = (total + 31) / 32;
+      for (int i = m; i < words; i += 128) cover[i] = 0u;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (qvalid) {
+        const int r0 = (max(my_cy - p.rf, 0) - y_lo) >> p.bh_shift, r1 = (min(my_cy + p.rf, p.H - 1) - y_lo) >> p.bh_shift;
+        const int c0 = (max(my_cx - p.rf, 0) - x_lo) >> 4, c1 = (min(my_cx + p.rf, p.W - 1) - x_lo) >> 4;
+        for (int r = r0; r <= r1; ++r)
+          for (int c = c0; c <= c1; ++c) {
+            const int i = r * ncols + c;
+            atomicOr(cover + (i >> 5), 1u << (i & 31));
+          }
       }
-      if (lane == 0) { nbox[0] = cnt; nbox[1] = 0; }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 2) {
+        int kept = 0;
+        for (int i = lane; i < words; i += 32) kept += __popc(cover[i]);
+        kept = __reduce_add_sync(0xffffffffu, kept);
+        const int k_lo = (int)((int64_t)kept * blockIdx.z / p.chunks), k_hi = (int)((int64_t)kept * (blockIdx.z + 1) / p.chunks);
+        int seen = 0;
+        for (int base = 0; base < total; base += 32) {
+          const int i = base + lane;
+          const bool keep = i < total && ((cover[i >> 5] >> (i & 31)) & 1u);
+          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+          const int pos = seen + __popc(bal & ((1u << lane) - 1u));
+          if (keep && pos >= k_lo && pos < k_hi && pos - k_lo < 2 * MAX_BOXES) {
+            const int by = y_lo + (i / ncols) * p.BH, bx = x_lo + (i % ncols) * 16;
+            boxes[pos - k_lo] = (uint32_t)by | ((uint32_t)bx << 16);
+          }
+          seen += __popc(bal);
+        }
+        cnt = min(k_hi - k_lo, 2 * MAX_BOXES);
+      }
     }
+    if (warp == 2 && lane == 0) { nbox[0] = cnt; nbox[1] = 0; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the ring before the TMA writes
   }
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
@@ -919,6 +948,8 @@ int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, i
   p.chunks = chunks;
   p.tiles_x = cdiv(Wc, p.QW);
   p.job = job; p.ent = mem_feat; p.best = best; p.tv = tv; p.ti = ti;
+  static const int exp_win = getenv("FGVC_TC16_EXP_WIN") ? atoi(getenv("FGVC_TC16_EXP_WIN")) : 0;   // perf experiments only
+  p.exp_flags = exp_win;
   // worst case (scattered arg-max keys): the entry lists every box of the frame
   FGVC_CHECK_ARG(rf >= 0 && rf <= 126, "c2f window engine: radius_fine %d too large", rf);
   if ((int64_t)cdiv(Hf, p.BH) * cdiv(Wf, 16) > 2 * MAX_BOXES) {

@@ -229,8 +229,9 @@ static int launch_fine(const void* fine_bank, int Hc, int Wc, int Hf, int Wf, in
 using namespace fgvc;
 
 extern "C" int64_t fgvc_c2f_scratch_elems(int32_t n_mem, int32_t n_coarse) {
-  // coarse per-frame arg-max table + the fine top-K lists (K <= 16) of up to 4 chunk CTAs per memory entry
-  return ((int64_t)n_mem + (int64_t)n_mem * 4 * 16) * n_coarse;
+  // coarse per-frame arg-max table + one floor per coarse query + the fine top-K lists (K <= 16) of up to 4 chunk
+  // CTAs per memory entry
+  return ((int64_t)n_mem + 1 + (int64_t)n_mem * 4 * 16) * n_coarse;
 }
 
 extern "C" int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, int32_t n_slots, int32_t Hc, int32_t Wc,
@@ -261,12 +262,13 @@ extern "C" int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, 
   static const bool no_window = getenv("FGVC_C2F_SIMT") != nullptr;
   if (!no_window && engine != FGVC_ENGINE_SIMT && bank_format == FGVC_BANK_F16 &&
       c2f_window_supported(Hf, Wf, Cf, K, n_mem)) {
-    float* fv = scratch_val + (int64_t)n_mem * Hc * Wc;          // fine lists live behind the coarse arg-max table
-    int32_t* fi = scratch_idx + (int64_t)n_mem * Hc * Wc;
+    float* floor_ws = scratch_val + (int64_t)n_mem * Hc * Wc;    // behind the coarse arg-max table: the floors,
+    float* fv = floor_ws + (int64_t)Hc * Wc;                     // then the fine lists
+    int32_t* fi = scratch_idx + (int64_t)(n_mem + 1) * Hc * Wc;
     const int chunks = c2f_window_chunks(Hc, Wc, n_mem);
     const int n_lists = n_mem * chunks;
     rc = launch_c2f_window_tc16(fine_bank, n_slots, Hc, Wc, Hf, Wf, Cf, scale, *job_host, mem_feat_slot, scratch_idx,
-                                radius_fine, K, chunks, fv, fi, st);
+                                radius_fine, K, chunks, floor_ws, fv, fi, st);
     if (rc == FGVC_OK) {
       if (K <= 4) return launch_tail<4>(fv, fi, K, n_lists, Hc, Wc, Hf, Wf, scale, *job_host, mem_label_slot, scratch_idx, radius_fine, temperature, fine_lab_bank, Lp, out, st);
       if (K <= 10) return launch_tail<10>(fv, fi, K, n_lists, Hc, Wc, Hf, Wf, scale, *job_host, mem_label_slot, scratch_idx, radius_fine, temperature, fine_lab_bank, Lp, out, st);

@@ -168,7 +168,7 @@ int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W
 bool c2f_window_supported(int Hf, int Wf, int Cf, int K, int n_mem);
 int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
                            const fgvc_job& job, const int32_t* mem_feat, const int32_t* best, int rf, int K, int chunks,
-                           float* tv, int32_t* ti, cudaStream_t st);
+                           float* floor_ws, float* tv, int32_t* ti, cudaStream_t st);
 int c2f_window_chunks(int Hc, int Wc, int n_mem);
 int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin, int job_end, int L, int Lp, int H,
                        int W, int out_h, int out_w, uint32_t* minmax, uint8_t* masks, cudaStream_t st);

@@ -155,15 +155,19 @@ __device__ __forceinline__ void cell_range(int i0, int in_size, int out_size, fl
   while (g > 0 && lerp_coord(g - 1, scale, in_size).i0 >= i0) --g;
   while (g < out_size - 1 && lerp_coord(g, scale, in_size).i0 < i0) ++g;
   *lo = g;                       // first o with i0(o) >= i0
-  int h = g;
+  // last o with i0(o) <= i0: analytic estimate (the last rows / columns all clamp to in_size - 1), then the same
+  // exact correction by search
+  int h = i0 >= in_size - 1 ? out_size - 1 : (int)ceilf(((float)i0 + 1.5f) / scale - 0.5f) - 1;
+  h = max(g, min(out_size - 1, h));
+  while (h > g && lerp_coord(h, scale, in_size).i0 > i0) --h;
   while (h < out_size - 1 && lerp_coord(h + 1, scale, in_size).i0 <= i0) ++h;
   *hi = h;
 }
 
 // Soft-argmax of the bilinearly up-sampled map WITHOUT evaluating every output pixel.  An up-sampled
 // value is a convex combination of its 4 taps, so it cannot exceed their maximum:
-//   1. seed: the largest SOURCE pixel (found while the map is staged in shared memory); one warp evaluates the
-//      output pixels around it; tau = the topk-th best up-sampled value found there -- `topk` distinct outputs
+//   1. seed: the largest SOURCE pixel (found while the map is streamed); the 5 x 5 output pixels nearest to it are
+//      evaluated; tau = the topk-th best up-sampled value found there -- `topk` distinct outputs
 //      reach it, so it is a lower bound of the final topk-th value, whatever set of outputs was looked at;
 //   2. scan the source cells; only cells whose largest tap reaches tau (minus a rounding margin) can hold a
 //      winner -- evaluate just those (each output belongs to exactly one cell, so none is seen twice).
@@ -235,6 +239,7 @@ __device__ __forceinline__ void list_hot_cells(const BilinearSrc& src, int i, fl
 constexpr int MAPS_PER_CTA = 8;
 constexpr int SLOTS = 32;          // per-lane slot maxima kept in shared memory (4 KB per map)
 
+// blockDim.x / 32 maps per CTA (<= MAPS_PER_CTA)
 __global__ void __launch_bounds__(32 * MAPS_PER_CTA)
 heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, int out_h, int out_w, int topk,
                       float* __restrict__ out_xy) {
@@ -244,7 +249,7 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
   __shared__ uint2 cells_s[MAPS_PER_CTA][CELL_CAP];
   __shared__ int n_cells_s[MAPS_PER_CTA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int map = blockIdx.x * MAPS_PER_CTA + warp;
+  const int map = blockIdx.x * (blockDim.x >> 5) + warp;
   if (map >= n_maps) return;
   float* win_v = win_v_s[warp];
   int* win_i = win_i_s[warp];
@@ -311,7 +316,8 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
   top.init();
   {
     const int sy = bi / W, sx = bi - sy * W;
-    const int ry = (int)ceilf(1.f / src.sy) + 1, rx = (int)ceilf(1.f / src.sx) + 1;
+    // (the 5 x 5 outputs nearest to the seed pixel's centre: one per lane)
+    const int ry = 2, rx = 2;
     const int cy = (int)(((float)sy + 0.5f) / src.sy), cx = (int)(((float)sx + 0.5f) / src.sx);
     const int y0 = max(cy - ry, 0), y1 = min(cy + ry, out_h - 1), x0 = max(cx - rx, 0), x1 = min(cx + rx, out_w - 1);
     const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
@@ -612,8 +618,11 @@ extern "C" int fgvc_heatmap_coords(const float* maps, int32_t n_maps, int32_t H,
   FGVC_CHECK_ARG(maps && out_xy && n_maps > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0,
                  "fgvc_heatmap_coords: bad arguments");
   FGVC_CHECK_ARG(topk >= 1 && topk <= CK, "fgvc_heatmap_coords: topk=%d not in [1,%d]", topk, CK);
-  heatmap_coords_kernel<<<cdiv(n_maps, MAPS_PER_CTA), 32 * MAPS_PER_CTA, 0, (cudaStream_t)stream>>>(
-      maps, n_maps, H, W, out_h, out_w, topk, out_xy);
+  // few maps: spread them over the SMs (a map's critical path is one warp's)
+  int mpc = MAPS_PER_CTA;
+  while (mpc > 1 && cdiv(n_maps, mpc) < 2 * 148) mpc >>= 1;
+  heatmap_coords_kernel<<<cdiv(n_maps, mpc), 32 * mpc, 0, (cudaStream_t)stream>>>(maps, n_maps, H, W, out_h, out_w, topk,
+                                                                                  out_xy);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }

@@ -65,6 +65,7 @@ struct Params {
   int HQ, WQ, scale, rf, chunks;
   fgvc_job job;
   const int32_t* best;              // [n_mem][HQ * WQ] coarse arg-max key pixel per memory entry
+  const float* floor;               // [HQ * WQ] lower bound of the query's final K-th value (accumulator units) or nullptr
   float* tv;
   int32_t* ti;
   float* dbg;
@@ -562,7 +563,8 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     TopK<K> top;
     top.init();
     volatile float* thr_mine = thr_sh + m * EPI_WG + wg;
-    *thr_mine = -INFINITY;
+    // window mode: every list of this query starts from a floor that K genuine candidates are known to reach
+    *thr_mine = (WIN && p.floor != nullptr && qvalid) ? __ldg(p.floor + qy * p.WQ + qx) : -INFINITY;
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     // Warpgroup wg owns the key rows wg (and wg + 4 when a box has 8 rows) of every box: a static assignment, so the
     // order in which a query's candidates reach its lists -- and with it the choice among exactly tied values -- does
@@ -921,6 +923,86 @@ bool c2f_window_supported(int Hf, int Wf, int Cf, int K, int n_mem) {
          (int64_t)n_mem * Hf * Wf < (1ll << 31);
 }
 
+// c2f fine stage: a lower bound of every coarse query's final K-th fine affinity that holds across ALL the CTAs
+// (memory entries x box chunks) working on the query.  The fine lists of a (tile, entry, chunk) CTA start cold and see
+// only a few hundred candidates, so without it ~45 of them are inserted per list, 5-16 lock-step insertion rounds per
+// key row (profiles/r2_d_point_tail.md).  Exactly scored here: the window centre and its 4 neighbours in every memory
+// entry (in-image, in-window, distinct candidates); the K-th largest of them, minus a rounding margin, is reached by
+// K genuine candidates.  One warp per coarse query, accumulator units (256 x affinity), same three products as the MMA.
+constexpr int FLOOR_SAMPLES = 5;
+__global__ void __launch_bounds__(256)
+c2f_floor_kernel(const __half* __restrict__ bank, int Hf, int Wf, int Cf, int HQ, int WQ, int scale, int rf,
+                 fgvc_job job, const int32_t* __restrict__ ent, const int32_t* __restrict__ best, int K,
+                 float* __restrict__ floor_out) {
+  // one CTA per coarse query, one warp per memory entry (8 at a time), the 5 samples of an entry in flight together
+  __shared__ float samp[tc16::TW_MAX_MEM * FLOOR_SAMPLES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x, nq = HQ * WQ;
+  const int qy = q / WQ, qx = q - qy * WQ;
+  const int64_t n_pix = (int64_t)Hf * Wf;
+  const __half* qrow = bank + ((int64_t)job.q_slot * 2 * n_pix + (int64_t)(qy * scale) * Wf + qx * scale) * Cf;
+  const __half* qlo = qrow + n_pix * Cf;
+  const int n_mem = job.mem_end - job.mem_begin;
+  float2 hq[4], lq[4];                                  // Cf <= 256: <= 4 channel pairs per lane
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = 2 * lane + 64 * i;
+    hq[i] = c < Cf ? __half22float2(*reinterpret_cast<const __half2*>(qrow + c)) : make_float2(0.f, 0.f);
+    lq[i] = c < Cf ? __half22float2(*reinterpret_cast<const __half2*>(qlo + c)) : make_float2(0.f, 0.f);
+  }
+  for (int e = warp; e < n_mem; e += 8) {
+    const int b = max(__ldg(best + (int64_t)e * nq + q), 0) % nq;
+    const int cy = (b / WQ) * scale, cx = (b % WQ) * scale;
+    const int slot = __ldg(ent + job.mem_begin + e) & ~FGVC_MEM_UNMASKED;
+    float acc[FLOOR_SAMPLES];
+    bool ok[FLOOR_SAMPLES];
+#pragma unroll
+    for (int sidx = 0; sidx < FLOOR_SAMPLES; ++sidx) {
+      const int dy = sidx == 3 ? 1 : (sidx == 4 ? -1 : 0), dx = sidx == 1 ? 1 : (sidx == 2 ? -1 : 0);
+      const int py = cy + dy, px = cx + dx;
+      ok[sidx] = py >= 0 && py < Hf && px >= 0 && px < Wf && abs(dy) <= rf && abs(dx) <= rf;      // warp-uniform
+      acc[sidx] = 0.f;
+      if (!ok[sidx]) continue;
+      const __half* krow = bank + ((int64_t)slot * 2 * n_pix + (int64_t)py * Wf + px) * Cf;
+      const __half* klo = krow + n_pix * Cf;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 2 * lane + 64 * i;
+        if (c < Cf) {
+          const float2 hk = __half22float2(*reinterpret_cast<const __half2*>(krow + c));
+          const float2 lk = __half22float2(*reinterpret_cast<const __half2*>(klo + c));
+          acc[sidx] += hq[i].x * hk.x + hq[i].x * lk.x + lq[i].x * hk.x + hq[i].y * hk.y + hq[i].y * lk.y + lq[i].y * hk.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int sidx = 0; sidx < FLOOR_SAMPLES; ++sidx) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[sidx] += __shfl_xor_sync(0xffffffffu, acc[sidx], o);
+      if (lane == 0) samp[e * FLOOR_SAMPLES + sidx] = ok[sidx] ? acc[sidx] : -INFINITY;
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  // the K-th largest sample: the one with exactly K - 1 samples ahead of it (ties broken by position);
+  // -inf (invalid positions, or fewer than K valid samples) = no floor
+  const int n = n_mem * FLOOR_SAMPLES;
+  float kth = -INFINITY;
+  for (int i = lane; i < n; i += 32) {
+    const float v = samp[i];
+    int ahead = 0;
+    for (int j = 0; j < n; ++j) {
+      const float u = samp[j];
+      ahead += (u > v || (u == v && j < i)) ? 1 : 0;
+    }
+    if (ahead == K - 1) kth = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+  if (kth > -INFINITY) kth -= 0.05f + 1e-5f * fabsf(kth);           // summation order of the MMA vs this loop
+  if (lane == 0) floor_out[q] = kth;
+}
+
 // how many CTAs share one (tile, entry): fill the chip, at most 4 (the tail merges n_mem * chunks lists per query)
 int c2f_window_chunks(int Hc, int Wc, int n_mem) {
   const long tiles = (long)cdiv(Hc, 8) * cdiv(Wc, 16);
@@ -932,7 +1014,7 @@ int c2f_window_chunks(int Hc, int Wc, int n_mem) {
 // fine keys (idx = memory position * Hf * Wf + fine key pixel).  best: [n_mem][Hc * Wc] coarse arg-max keys.
 int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, int Hf, int Wf, int Cf, int scale,
                            const fgvc_job& job, const int32_t* mem_feat, const int32_t* best, int rf, int K, int chunks,
-                           float* tv, int32_t* ti, cudaStream_t st) {
+                           float* floor_ws, float* tv, int32_t* ti, cudaStream_t st) {
   using namespace tc16;
   Params p = {};
   p.H = Hf; p.W = Wf; p.C = Cf; p.n_pix = Hf * Wf;
@@ -959,6 +1041,13 @@ int launch_c2f_window_tc16(const void* fine_bank, int n_slots, int Hc, int Wc, i
   CUtensorMap mk;
   int rc = make_map16(&mk, fine_bank, n_slots, Hf, Wf, Cf, p.BH);
   if (rc) return rc;
+  static const bool no_floor = getenv("FGVC_C2F_NOFLOOR") != nullptr;     // perf experiments only
+  if (floor_ws != nullptr && !no_floor) {
+    c2f_floor_kernel<<<Hc * Wc, 256, 0, st>>>(reinterpret_cast<const __half*>(fine_bank), Hf, Wf, Cf, Hc, Wc, scale,
+                                                      rf, job, mem_feat, best, K, floor_ws);
+    FGVC_LAUNCH_CHECK();
+    p.floor = floor_ws;
+  }
   dim3 grid(cdiv(Hc, p.QH) * p.tiles_x, job.mem_end - job.mem_begin, chunks);
   return launch_by_k<1, true>(mk, fine_bank, p, grid, K, st);
 }

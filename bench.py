@@ -42,12 +42,12 @@ CFG = dict(precede_frames=WORK["precede_frames"], topk=WORK["topk"], temperature
            neighbor_range=WORK["neighbor_range"], with_first=True, with_first_neighbor=True)
 
 
-def in_mask_pairs(H, W, r):
-    """sum over queries of in-mask keys = |{(q,k): dy^2+dx^2 < r^2}| (exact)."""
+def in_mask_pairs(H, W, r, square=False):
+    """sum over queries of in-mask keys = |{(q,k): dy^2+dx^2 < r^2}| (exact); square: |dy|, |dx| <= r."""
     n = 0
-    for dy in range(-(r - 1), r):
-        for dx in range(-(r - 1), r):
-            if dy * dy + dx * dx < r * r:
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            if (square or dy * dy + dx * dx < r * r):
                 n += max(0, H - abs(dy)) * max(0, W - abs(dx))
     return n
 
@@ -424,6 +424,8 @@ SECONDARY = {
     # TAP-Vid-Kinetics shape: ONE 250-frame clip, 1024 points, two-phase split over the ranks, memory-length sweep
     "cfg5_tapvid_kinetics": dict(hw=(256, 256), T=250, P=1024, nr=30, precede=[5, 10, 20, 40], clips=None,
                                  scaling="strong"),
+    # local-window ("HR", correlation) tracker on the TAP-Vid-DAVIS shape: (2r + 1)^2 window, r = 12, zero-padded borders
+    "hr_local_window": dict(hw=(256, 256), T=50, P=256, nr=24, precede=[5], clips=None, scaling="weak", tracker="hr"),
 }
 
 
@@ -449,7 +451,7 @@ def run_secondary(dev, rank, world, args):
     res = {}
     pk = peaks()
     for name, c in SECONDARY.items():
-        if args.only and name.split("_")[0] not in args.only:
+        if args.only and name.split("_")[0] not in args.only and name not in args.only:
             continue
         h, w = c["hw"]
         Hf, Wf = h // 2, w // 2
@@ -458,12 +460,13 @@ def run_secondary(dev, rank, world, args):
         feats_host = [f.cpu().pin_memory() for f in feats_list]
         qp = S.query_points(c["P"], c["T"], h, w, seed=1)
         groups = [(0, qp[:, 1:].to(dev))]
-        pairs = in_mask_pairs(Hf, Wf, c["nr"] // 2)
+        pairs = in_mask_pairs(Hf, Wf, c["nr"] // 2, square=c.get("tracker") == "hr")
         sweep = []
         for precede in c["precede"]:
             cfg = dict(precede_frames=precede, topk=10, temperature=0.07, neighbor_range=c["nr"], with_first=True,
                        with_first_neighbor=True)
-            trk = fgvc_b200.VanillaTracker(backbone=torch.nn.Identity(), test_cfg=cfg)
+            cls = fgvc_b200.HRVanillaTracker if c.get("tracker") == "hr" else fgvc_b200.VanillaTracker
+            trk = cls(backbone=torch.nn.Identity(), test_cfg=cfg)
             my_clips = [0] if c["clips"] is None else list(range(rank, c["clips"], world))
             shard = (rank, world) if (c["clips"] is None and c["scaling"] == "strong" and world > 1) else None
 
@@ -503,6 +506,8 @@ def run_secondary(dev, rank, world, args):
             ms = _max_over_ranks(e0.elapsed_time(e1), dev, world) / reps
             k1_ms = sum(a.elapsed_time(b) for a, b in k1_ev) / reps
             k1_ms = _max_over_ranks(k1_ms, dev, world)
+            one_pass(True)                                   # untimed: first-touch of the staging buffers
+            torch.cuda.synchronize()
             if world > 1:
                 _dist().barrier()
             e0.record()

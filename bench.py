@@ -473,7 +473,9 @@ def run_secondary(dev, rank, world, args):
             def one_pass(from_host):
                 outs = []
                 for ci in my_clips:
-                    if from_host:
+                    if from_host and shard is None:
+                        f = feats_host[ci % n_distinct]       # pinned host tensor: staged in chunks by the tracker
+                    elif from_host:
                         f = torch.empty_like(feats_list[ci % n_distinct])
                         f.copy_(feats_host[ci % n_distinct], non_blocking=True)
                     else:
@@ -533,7 +535,7 @@ def run_secondary(dev, rank, world, args):
                          parallelism=("two-phase split of one video: K1 sharded over frame ranges, lists all-gathered, "
                                       "tail sharded over points" if c["clips"] is None and c["scaling"] == "strong"
                                       else "clips sharded rank-strided, results gathered in dataset order"),
-                         e2e_note="host features in (pinned, copied inside the timed pass), host tracks out",
+                         e2e_note="host features in (pinned, copied inside the timed pass in frame chunks that overlap K0 / K1 of the frames already on the device), host tracks out",
                          results=sweep if len(sweep) > 1 else sweep[0])
         del feats_list, feats_host
         torch.cuda.empty_cache()

@@ -121,6 +121,45 @@ class VanillaTracker(nn.Module):
         cur.wait_stream(side)
         return bank
 
+    def _stream_in(self, feats_host, bank, table, t0, radius, mask_mode, normalize, n_chunks=6):
+        """Host features of ONE clip -> feature bank and top-k lists, pipelined: the frames are copied in chunks on a
+        side stream (two staging buffers); on the compute stream K0 of a chunk and K1 of the jobs whose query frame
+        lies in it follow as soon as it has landed (a job only reads frames before its own), so the host link and the
+        kernels overlap inside a single clip.  Same lists as one K1 launch over the whole table."""
+        cfg = self.test_cfg
+        dev = bank.buf.device
+        T = feats_host.shape[0]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cp = self._copy_stream
+        plan = engine.plan_k1(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id)
+        lists = engine.TopKLists(len(table), plan.lists_per_job, bank.H * bank.W, cfg.topk, dev)
+        step = -(-T // n_chunks)
+        stage = [torch.empty((step,) + tuple(feats_host.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+        free = [None, None]
+        cp.wait_stream(cur)
+        for i, a in enumerate(range(0, T, step)):
+            b = min(T, a + step)
+            buf = stage[i % 2][:b - a]
+            with torch.cuda.stream(cp):
+                if free[i % 2] is not None:
+                    cp.wait_event(free[i % 2])            # K0 of the chunk that used this buffer has read it
+                buf.copy_(feats_host[a:b], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cp)
+            cur.wait_event(ready)
+            bank.load_frames(buf, a, normalize=normalize)
+            free[i % 2] = torch.cuda.Event()
+            free[i % 2].record(cur)
+            j0, j1 = max(a, t0 + 1) - (t0 + 1), b - (t0 + 1)   # jobs of this group: job j <-> query frame t0 + 1 + j
+            if j1 > j0:
+                engine.affinity_topk(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id, lists=lists,
+                                     job_range=(j0, j1), plan=plan)
+        for s_ in stage:
+            s_.record_stream(cp)
+        return lists
+
     # --------------------------------------------------------------------- propagation
     two_phase_sharding = True      # apis.sharded_forward_test: forward_test(..., shard=(rank, world))
     local_window = False           # HRVanillaTracker: square window + zero-padded candidates
@@ -133,6 +172,7 @@ class VanillaTracker(nn.Module):
         this rank's frame range only and the top-k lists are all-gathered; the recurrent tail runs for this rank's
         slice of every group's points and the tracks are all-gathered.  Every rank returns the full result."""
         cfg = self.test_cfg
+        host_feats = False
         if isinstance(feats, FeatureBank):               # encode_to_bank: K0 already ran, overlapped with the encoder
             pre_bank = feats
             T, C, Hf, Wf, dev = pre_bank.n_slots, pre_bank.C, pre_bank.H, pre_bank.W, pre_bank.buf.device
@@ -140,6 +180,9 @@ class VanillaTracker(nn.Module):
             pre_bank = None
             T, C, Hf, Wf = feats.shape
             dev = feats.device
+            if not feats.is_cuda:                        # host features (pinned): staged in frame chunks, see below
+                _lib.require_cuda()
+                host_feats, dev = True, torch.device("cuda", torch.cuda.current_device())
         h, w = image_hw
         stride = h // Hf
         precede = cfg.precede_frames
@@ -163,11 +206,13 @@ class VanillaTracker(nn.Module):
                 raise TypeError("the local-window tracker needs neighbor_range")
             # window positions outside the image stay candidates (affinity 0, value 0): merged by the gather
             flags |= _lib.zero_pad_flags(nr // 2, Wf)
+        normalize = cfg.get("with_norm", cfg.get("withnorm", True))
         if pre_bank is not None:
             bank = pre_bank
         else:
             bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
-            bank.load_frames(feats, 0, normalize=cfg.get("with_norm", cfg.get("withnorm", True)))
+            if not host_feats:
+                bank.load_frames(feats, 0, normalize=normalize)
 
         table = JobTable()
         spans = []   # per group: (first job, t0)
@@ -180,7 +225,12 @@ class VanillaTracker(nn.Module):
         radius = (nr // 2) if nr is not None else 1
         shared = None
         rank, world = shard if shard is not None else (0, 1)
-        if len(table) == 0:
+        streamed = host_feats and len(groups) == 1 and world == 1 and len(table) > 0
+        if host_feats and not streamed:
+            bank.load_frames(feats.to(dev, non_blocking=True), 0, normalize=normalize)
+        if streamed:
+            lists = self._stream_in(feats, bank, table, groups[0][0], radius, mask_mode, normalize)
+        elif len(table) == 0:
             lists = None
         elif world > 1:
             from . import apis

@@ -281,3 +281,22 @@ def test_hr_vos_entry_matches_oracle_loop():
     # a padded clip with another original size goes through the reference's resize chain: shape and frame 0 only
     out2 = trk.forward_test_vos(imgs[..., :47, :63], seg[None, :47, :63], [dict(original_shape=(60, 80, 3))])
     assert out2[0].shape == (T, 60, 80)
+
+
+@pytest.mark.gpu
+def test_host_features_staged_in_chunks_equal_resident_run():
+    """propagate_points with pinned HOST features (chunked copy overlapped with K0 / K1 over job ranges) returns
+    exactly what the resident call returns, for the global and the local-window tracker."""
+    import fgvc_b200
+    g = torch.Generator().manual_seed(5)
+    T, C, Hf, Wf, stride = 23, 64, 24, 32, 4
+    feats = _coherent(g, T, C, Hf, Wf)
+    h, w = Hf * stride, Wf * stride
+    pts = torch.rand(7, 2, generator=g) * torch.tensor([w - 1.0, h - 1.0])
+    cfg = dict(precede_frames=6, topk=10, temperature=0.07, neighbor_range=10, with_first=True, with_first_neighbor=True)
+    for cls in (fgvc_b200.VanillaTracker, fgvc_b200.HRVanillaTracker):
+        trk = cls(backbone=torch.nn.Identity(), test_cfg=cfg)
+        for t0 in (0, 5):
+            want = trk.propagate_points(feats.cuda(), [(t0, pts)], (h, w))[0]
+            got = trk.propagate_points(feats.pin_memory(), [(t0, pts)], (h, w))[0]
+            assert torch.equal(got, want), (cls.__name__, t0)

@@ -31,6 +31,52 @@ class C2FPointTracker:
         self.cfg = cfg
         self.engine_id = engine_id
 
+    def _stage(self, feats_coarse, feats_fine, coarse, fine, normalize, n_chunks=6):
+        """K0 of both feature stacks.  Device tensors: two launches, returns a no-op.  Host (pinned) tensors: chunked
+        copies on a side stream + K0 per chunk on a second one; returns ``landed(t)``, which makes the current stream
+        wait for the chunk frame t is in."""
+        if feats_coarse.is_cuda and feats_fine.is_cuda:
+            coarse.load_frames(feats_coarse.float(), 0, normalize=normalize)
+            fine.load_frames(feats_fine.float(), 0, normalize=normalize)
+            return lambda t: None
+        dev = coarse.buf.device
+        T = feats_coarse.shape[0]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream, self._k0_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        cp, k0 = self._copy_stream, self._k0_stream
+        step = -(-T // n_chunks)
+        cp.wait_stream(cur)
+        k0.wait_stream(cur)
+        done = []
+        for a in range(0, T, step):
+            b = min(T, a + step)
+            with torch.cuda.stream(cp):
+                fc = feats_coarse[a:b].to(dev, non_blocking=True)
+                ff = feats_fine[a:b].to(dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cp)
+            with torch.cuda.stream(k0):
+                k0.wait_event(ready)
+                coarse.load_frames(fc.float(), a, normalize=normalize)
+                fine.load_frames(ff.float(), a, normalize=normalize)
+                ev = torch.cuda.Event()
+                ev.record(k0)
+            fc.record_stream(k0)
+            ff.record_stream(k0)
+            done.append((b, ev))
+        state = {"i": 0}
+
+        def landed(t):
+            while state["i"] < len(done) and done[state["i"]][0] <= t:
+                state["i"] += 1                      # chunks wholly before frame t: already waited for, or implied
+            # frame t lies in chunk i (its end is the first one > t): wait for it (events of earlier chunks precede it
+            # on the same stream)
+            if state["i"] < len(done) and not state.get(state["i"]):
+                cur.wait_event(done[state["i"]][1])
+                state[state["i"]] = True
+        return landed
+
     @torch.no_grad()
     def track(self, feats_coarse, feats_fine, points_xy, image_hw):
         """feats_coarse [T,C,Hc,Wc], feats_fine [T,Cf,Hf,Wf] (CUDA fp32, Hf = s * Hc); points_xy [P,2] (x, y) image
@@ -41,14 +87,15 @@ class C2FPointTracker:
         Tf, Cf, Hf, Wf = feats_fine.shape
         assert T == Tf and Hf % Hc == 0 and Wf % Wc == 0 and Hf // Hc == Wf // Wc, "fine grid must be s x the coarse grid"
         h, w = image_hw
-        dev = feats_coarse.device
+        dev = feats_coarse.device if feats_coarse.is_cuda else torch.device("cuda", torch.cuda.current_device())
         stride_f = h // Hf
         split = cfg.get("split") or ("f16" if (engine.default_split(C) == "f16" and Cf % 4 == 0) else "tf32")
         normalize = cfg.get("with_norm", True)
         coarse = FeatureBank(T, C, Hc, Wc, dev, split=split)
-        coarse.load_frames(feats_coarse.float(), 0, normalize=normalize)
         fine = FeatureBank(T, Cf, Hf, Wf, dev, split=split)
-        fine.load_frames(feats_fine.float(), 0, normalize=normalize)
+        # host features: copied in frame chunks on a side stream; the frame loop below waits for the chunk a frame is in
+        # (frame t only reads frames <= t), so the host link overlaps the propagation of the frames already there
+        landed = self._stage(feats_coarse, feats_fine, coarse, fine, normalize)
         P = points_xy.shape[0]
         pts = points_xy.to(device=dev, dtype=torch.float32).contiguous()
         labels = LabelBank(T, P, Hf, Wf, dev)
@@ -64,6 +111,7 @@ class C2FPointTracker:
         maps = torch.empty(P, Hc, Wc, dtype=torch.float32, device=dev)
         outs = []
         for t in range(1, T):
+            landed(t)
             out = engine.c2f_propagate(coarse, fine, table, t - 1, labels, radius, cfg.get("radius_fine", 12),
                                        cfg["topk"], cfg["temperature"], cfg.get("mask_mode", "circle"), self.engine_id)
             # the coarse output becomes (a) the fine memory labels of the following frames, (b) this frame's coordinates

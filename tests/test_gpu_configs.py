@@ -300,3 +300,18 @@ def test_host_features_staged_in_chunks_equal_resident_run():
             want = trk.propagate_points(feats.cuda(), [(t0, pts)], (h, w))[0]
             got = trk.propagate_points(feats.pin_memory(), [(t0, pts)], (h, w))[0]
             assert torch.equal(got, want), (cls.__name__, t0)
+
+
+@pytest.mark.gpu
+def test_c2f_driver_host_features_equal_resident_run():
+    import fgvc_b200
+    g = torch.Generator().manual_seed(9)
+    T, C, Hc, Wc, s = 9, 64, 8, 12, 4
+    fc, ff = _coherent(g, T, C, Hc, Wc), _coherent(g, T, C, Hc * s, Wc * s)
+    h, w = Hc * s * 2, Wc * s * 2
+    pts = torch.rand(5, 2, generator=g) * torch.tensor([w - 1.0, h - 1.0])
+    cfg = dict(precede_frames=3, topk=10, temperature=0.07, neighbor_range=6, radius_fine=5, with_first=True)
+    trk = fgvc_b200.C2FPointTracker(cfg)
+    want = trk.track(fc.cuda(), ff.cuda(), pts, (h, w))[0]
+    got = trk.track(fc.pin_memory(), ff.pin_memory(), pts, (h, w))[0]
+    assert torch.equal(got, want)

@@ -136,9 +136,14 @@ class VanillaTracker(nn.Module):
         plan = engine.plan_k1(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id)
         lists = engine.TopKLists(len(table), plan.lists_per_job, bank.H * bank.W, cfg.topk, dev)
         step = -(-T // n_chunks)
-        stage = [torch.empty((step,) + tuple(feats_host.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
-        free = [None, None]
-        cp.wait_stream(cur)
+        # the two staging buffers live across calls (a stream of clips): the first copy of the next clip then only waits
+        # for the K0 that last read its buffer, not for the previous clip's whole tail
+        key = (step,) + tuple(feats_host.shape[1:]) + (dev.index,)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [torch.empty(key[:-1], dtype=torch.float32, device=dev) for _ in range(2)]
+            self._stage_free, self._stage_key = [None, None], key
+            cp.wait_stream(cur)                           # fresh memory: earlier kernels of this stream may still use it
+        stage, free = self._stage, self._stage_free
         for i, a in enumerate(range(0, T, step)):
             b = min(T, a + step)
             buf = stage[i % 2][:b - a]
@@ -156,8 +161,6 @@ class VanillaTracker(nn.Module):
             if j1 > j0:
                 engine.affinity_topk(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id, lists=lists,
                                      job_range=(j0, j1), plan=plan)
-        for s_ in stage:
-            s_.record_stream(cp)
         return lists
 
     # --------------------------------------------------------------------- propagation

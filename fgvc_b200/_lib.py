@@ -55,6 +55,8 @@ SIGNATURES = {
     "fgvc_tc_supported": (I, [I, I, I, I, I]),
     "fgvc_topk_bytes": (L64, [I, I, I, I]),
     "fgvc_affinity_topk": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, I, P]),
+    "fgvc_affinity_topk_seeded": (I, [P, I, I, I, I, I, P, I, P, I, I, I, I, P, P, P, I, P]),
+    "fgvc_topk_floor": (I, [P, I, I, I, I, P, I, P, I, I, I, P, P]),
     "fgvc_affinity_topk_packed": (I, [P, I, I, I, I, P, P, I, P, P, I, I, I, I, I, I, P, P, P]),
     "fgvc_packed_tile_shape": (I, [I, I, I, I, I, P, P, P, P]),
     "fgvc_debug_affinity_boxes": (I, [P, I, I, I, I, I, P, I, P, I, I, I, P, P, P, P, I, P]),

@@ -61,7 +61,8 @@ static int pick_engine(int engine, int fmt, int H, int W, int C, int K, bool* us
 static int affinity_topk_impl(const void* feat_bank, int32_t fmt, int32_t n_slots, int32_t H, int32_t W, int32_t C,
                               const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot, int32_t radius,
                               int32_t mask_mode, int32_t K, int32_t groups, float* topk_val, int32_t* topk_idx,
-                              int32_t engine, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes, void* stream) {
+                              int32_t engine, float* dbg, int32_t* dbg_meta, int32_t dbg_max_boxes, void* stream,
+                              const float* floor = nullptr) {
   FGVC_CHECK_ARG(feat_bank && jobs && mem_feat_slot && topk_val && topk_idx, "fgvc_affinity_topk: null pointer");
   FGVC_CHECK_ARG(H > 0 && W > 0 && C > 0 && n_jobs > 0 && n_slots > 0, "fgvc_affinity_topk: bad shape");
   FGVC_CHECK_ARG(K >= 1 && K <= 16, "fgvc_affinity_topk: topk=%d not in [1,16]", K);
@@ -74,8 +75,9 @@ static int affinity_topk_impl(const void* feat_bank, int32_t fmt, int32_t n_slot
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc && fmt == FGVC_BANK_F16) {
+    // (the floor is an optional accelerator of the fp16 tensor engine; the other engines ignore it)
     rc = launch_affinity_topk_tc16(feat_bank, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
-                                   groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st);
+                                   groups, topk_val, topk_idx, dbg, dbg_meta, dbg_max_boxes, st, floor);
     if (rc != FGVC_ERR_UNSUPPORTED || engine != FGVC_ENGINE_AUTO) return rc;
     // a shape the tensor kernel does not take (e.g. a huge map with unmasked frames): CUDA-core engine
     return launch_affinity_topk_simt(feat_bank, fmt, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode, K,
@@ -94,6 +96,29 @@ extern "C" int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, in
                                   int32_t engine, void* stream) {
   return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
                             K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int fgvc_affinity_topk_seeded(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W,
+                                         int32_t C, const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                                         int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
+                                         const float* floor, float* topk_val, int32_t* topk_idx, int32_t engine,
+                                         void* stream) {
+  return affinity_topk_impl(feat_bank, bank_format, n_slots, H, W, C, jobs, n_jobs, mem_feat_slot, radius, mask_mode,
+                            K, groups, topk_val, topk_idx, engine, nullptr, nullptr, 0, stream, floor);
+}
+
+extern "C" int fgvc_topk_floor(const void* feat_bank, int32_t bank_format, int32_t H, int32_t W, int32_t C,
+                               const fgvc_job* jobs, int32_t n_jobs, const int32_t* seed_feat_slot, int32_t radius,
+                               int32_t mask_mode, int32_t K, float* floor_out, void* stream) {
+  FGVC_CHECK_ARG(feat_bank && jobs && seed_feat_slot && floor_out, "fgvc_topk_floor: null pointer");
+  FGVC_CHECK_ARG(H > 0 && W > 0 && C > 0 && n_jobs > 0 && K >= 1 && K <= 16 && radius >= 1, "fgvc_topk_floor: bad arguments");
+  FGVC_CHECK_ARG(mask_mode == FGVC_MASK_CIRCLE || mask_mode == FGVC_MASK_SQUARE, "fgvc_topk_floor: bad mask mode");
+  if (bank_format != FGVC_BANK_F16) {
+    set_error("fgvc_topk_floor: F16 bank only");
+    return FGVC_ERR_UNSUPPORTED;
+  }
+  return launch_topk_floor16(feat_bank, H, W, C, jobs, n_jobs, seed_feat_slot, radius, mask_mode, K, floor_out,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int fgvc_packed_tile_shape(int32_t H, int32_t W, int32_t radius, int32_t mask_mode, int32_t jobs_per_tile,

@@ -153,7 +153,9 @@ bool tc_supported(int H, int W, int C, int K);
 bool tc16_supported(int H, int W, int C, int K);
 int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
-                              float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st);
+                              float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st, const float* floor = nullptr);
+int launch_topk_floor16(const void* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs, const int32_t* seed_slot,
+                        int radius, int mode, int K, float* floor_out, cudaStream_t st);
 int64_t chain_workspace_bytes(int n_jobs, int n_pix, int K);
 int launch_gather_chain(const float* tv, const int32_t* ti, int K, int groups, const fgvc_job* jobs, int job_begin,
                         int job_end, const int32_t* mem_label, const int32_t* pair_ref, int n_pix, float temperature,

@@ -563,8 +563,11 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
     TopK<K> top;
     top.init();
     volatile float* thr_mine = thr_sh + m * EPI_WG + wg;
-    // window mode: every list of this query starts from a floor that K genuine candidates are known to reach
-    *thr_mine = (WIN && p.floor != nullptr && qvalid) ? __ldg(p.floor + qy * p.WQ + qx) : -INFINITY;
+    // every list of this query may start from a floor that K genuine candidates are known to reach (the caller's
+    // guarantee): [coarse query] in window mode, [job][query pixel] otherwise
+    *thr_mine = (p.floor != nullptr && qvalid)
+                    ? __ldg(p.floor + (WIN ? (int64_t)qy * p.WQ + qx : (int64_t)jb * p.n_pix + qy * p.W + qx))
+                    : -INFINITY;
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_WG) : "memory");
     // Warpgroup wg owns the key rows wg (and wg + 4 when a box has 8 rows) of every box: a static assignment, so the
     // order in which a query's candidates reach its lists -- and with it the choice among exactly tied values -- does
@@ -856,9 +859,10 @@ void packed_tile_shape(int H, int W, int reach, int jobs_per_tile, int* QH, int*
 static int launch_k1(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_z,
                      const fgvc_tile_group* tgroups, const int32_t* ent, const int32_t* upos, int jobs_per_tile,
                      int radius, int mode, int K, int lists_per_job, int split, float* tv, int32_t* ti, float* dbg,
-                     int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st) {
+                     int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st, const float* floor = nullptr) {
   using namespace tc16;
   Params p = {};
+  p.floor = floor;
   p.H = H; p.W = W; p.C = C; p.n_pix = H * W;
   p.radius = radius; p.mode = mode; p.reach = mask_reach(radius, mode);
   int ncta = 1;
@@ -893,9 +897,111 @@ static int launch_k1(const void* bank, int n_slots, int H, int W, int C, const f
 
 int launch_affinity_topk_tc16(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs, int n_jobs,
                               const int32_t* mem_feat, int radius, int mode, int K, int groups, float* tv, int32_t* ti,
-                              float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st) {
+                              float* dbg, int32_t* dbg_meta, int dbg_max_boxes, cudaStream_t st, const float* floor) {
   return launch_k1(bank, n_slots, H, W, C, jobs, n_jobs, nullptr, mem_feat, nullptr, 1, radius, mode, K, groups, groups,
-                   tv, ti, dbg, dbg_meta, dbg_max_boxes, st);
+                   tv, ti, dbg, dbg_meta, dbg_max_boxes, st, floor);
+}
+
+// A floor for the lists of every (job, query pixel): the K-th largest of the exactly scored 5 x 5 neighbourhood of the
+// query's own position in ONE memory frame of the job (seed_slot[job], e.g. the previous frame), restricted to
+// in-image, in-mask keys -- K genuine candidates of the job reach it.  For launches whose lists start cold and stay
+// short (one list per (query frame, memory frame) pair, shared between the point groups of a clip): without a floor
+// half of such a launch is lock-step list insertion.  One warp per query pixel, 8 channels per lane, accumulator
+// units (256 x affinity), the same three products as the MMA; -inf where fewer than K samples are valid.
+__global__ void __launch_bounds__(256)
+topk_floor_kernel(const __half* __restrict__ bank, int H, int W, int C, const fgvc_job* __restrict__ jobs,
+                  const int32_t* __restrict__ seed_slot, int radius, int mode, int K, float* __restrict__ floor_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_pix = H * W;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= n_pix) return;
+  const int job = blockIdx.y;
+  const int ss = __ldg(seed_slot + job);
+  float* out = floor_out + (int64_t)job * n_pix + q;
+  if (ss < 0) { if (lane == 0) *out = -INFINITY; return; }
+  const int qy = q / W, qx = q - qy * W;
+  const int64_t part = (int64_t)n_pix * C;
+  const bool act = 8 * lane < C;
+  float hq[8], lq[8];
+  {
+    const __half* row = bank + (int64_t)jobs[job].q_slot * 2 * part + (int64_t)q * C + 8 * lane;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (act) { a = __ldg(reinterpret_cast<const uint4*>(row)); b = __ldg(reinterpret_cast<const uint4*>(row + part)); }
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(ah[i]), y = __half22float2(bh[i]);
+      hq[2 * i] = x.x; hq[2 * i + 1] = x.y; lq[2 * i] = y.x; lq[2 * i + 1] = y.y;
+    }
+  }
+  float acc[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    acc[s] = 0.f;
+    if (s >= 25) continue;
+    const int py = qy + s / 5 - 2, px = qx + s % 5 - 2;
+    if (py < 0 || py >= H || px < 0 || px >= W || !act) continue;          // (validity is applied after the reduction)
+    const __half* row = bank + (int64_t)ss * 2 * part + ((int64_t)py * W + px) * C + 8 * lane;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row + part));
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 hk = __half22float2(ah[i]), lk = __half22float2(bh[i]);
+      t += hq[2 * i] * hk.x + hq[2 * i] * lk.x + lq[2 * i] * hk.x;
+      t += hq[2 * i + 1] * hk.y + hq[2 * i + 1] * lk.y + lq[2 * i + 1] * hk.y;
+    }
+    acc[s] = t;
+  }
+  // transposing reduction: 31 shuffles; afterwards lane s holds the full sum of sample s in acc[0]
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n / 2) {
+        const float send = upper ? acc[i] : acc[i + n / 2];
+        const float keep = upper ? acc[i + n / 2] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  float mine = -INFINITY;
+  if (lane < 25) {
+    const int dy = lane / 5 - 2, dx = lane % 5 - 2;
+    const int py = qy + dy, px = qx + dx;
+    const bool in_mask = mode == FGVC_MASK_CIRCLE ? dy * dy + dx * dx < radius * radius : (abs(dy) <= radius && abs(dx) <= radius);
+    if (py >= 0 && py < H && px >= 0 && px < W && in_mask) mine = acc[0];
+  }
+  const int n_valid = __popc(__ballot_sync(0xffffffffu, mine > -INFINITY));
+  int ahead = 0;
+#pragma unroll
+  for (int j = 0; j < 25; ++j) {
+    const float u = __shfl_sync(0xffffffffu, mine, j);
+    ahead += (u > mine || (u == mine && j < lane)) ? 1 : 0;
+  }
+  const uint32_t pick = __ballot_sync(0xffffffffu, lane < 25 && mine > -INFINITY && ahead == K - 1);
+  float kth = -INFINITY;
+  if (n_valid >= K && pick) kth = __shfl_sync(0xffffffffu, mine, __ffs(pick) - 1);
+  if (kth > -INFINITY) kth -= 0.05f + 1e-5f * fabsf(kth);        // summation order of the MMA vs this loop
+  if (lane == 0) *out = kth;
+}
+
+int launch_topk_floor16(const void* bank, int H, int W, int C, const fgvc_job* jobs, int n_jobs, const int32_t* seed_slot,
+                        int radius, int mode, int K, float* floor_out, cudaStream_t st) {
+  if (!tc16_supported(H, W, C, K)) {
+    set_error("fgvc_topk_floor: needs the F16 bank with C %% 64 == 0, C <= 256 (C=%d)", C);
+    return FGVC_ERR_UNSUPPORTED;
+  }
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    dim3 grid(cdiv(H * W, 8), min(65535, n_jobs - j0));
+    topk_floor_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(bank), H, W, C, jobs + j0, seed_slot + j0, radius,
+                                           mode, K, floor_out + (int64_t)j0 * H * W);
+    FGVC_LAUNCH_CHECK();
+  }
+  return FGVC_OK;
 }
 
 int launch_affinity_topk_tc16_packed(const void* bank, int n_slots, int H, int W, int C, const fgvc_job* jobs,

@@ -474,10 +474,11 @@ def plan_k1(bank, table, radius, K, mask_mode="circle", job_range=None, engine=_
 
 
 def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engine=_lib.ENGINE_AUTO, lists=None,
-                  job_range=None, pack=True, plan=None):
+                  job_range=None, pack=True, plan=None, floor=None):
     """K1 over every job of ``table`` (or the jobs ``job_range=(begin, end)``) in one launch.  ``AUTO``
     = the tensor engine of the bank format when the shape allows, else the CUDA-core engine.  ``plan`` (plan_k1)
-    fixes the tiling; the lists hold ``plan.lists_per_job`` partial lists per job, merged by the gather."""
+    fixes the tiling; the lists hold ``plan.lists_per_job`` partial lists per job, merged by the gather.
+    ``floor`` [jobs, Nq] (topk_floor): starting value of the lists, un-packed launches only (see the header)."""
     dev = bank.buf.device
     jobs, mem_feat, _ = table.device(dev)
     j0, j1 = job_range if job_range is not None else (0, len(table))
@@ -496,15 +497,32 @@ def affinity_topk(bank, table, radius, K, mask_mode="circle", groups=None, engin
         ev[0].record()
         try:
             return _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job,
-                                         jobs, mem_feat, dev)
+                                         jobs, mem_feat, dev, floor)
         finally:
             ev[1].record()
             K1_TIMING.append(ev)
     return _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job, jobs,
-                                 mem_feat, dev)
+                                 mem_feat, dev, floor)
 
 
-def _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job, jobs, mem_feat, dev):
+def topk_floor(bank, table, seed_slots, radius, K, mask_mode="circle"):
+    """fgvc_topk_floor: per (job, query pixel) the K-th best of the exactly scored 5 x 5 neighbourhood of the query's own
+    position in frame ``seed_slots[job]`` (< 0: none).  F16 bank with a tensor-engine shape only, else None."""
+    if bank.fmt != _lib.BANK_F16 or not tensor16_ok(bank, K, _lib.ENGINE_AUTO):
+        return None
+    dev = bank.buf.device
+    jobs, _, _ = table.device(dev)
+    seeds = torch.tensor(list(seed_slots), dtype=torch.int32, device=dev)
+    assert seeds.numel() == len(table)
+    out = torch.empty(len(table), bank.H * bank.W, dtype=torch.float32, device=dev)
+    mode = _lib.MASK_CIRCLE if mask_mode == "circle" else _lib.MASK_SQUARE
+    call("fgvc_topk_floor", ptr(bank.buf), bank.fmt, bank.H, bank.W, bank.C, ptr(jobs), len(table), ptr(seeds), int(radius),
+         mode, int(K), ptr(out), stream_ptr())
+    return out
+
+
+def _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j0, j1, plan, per_job, jobs, mem_feat, dev,
+                          floor=None):
     # fp16 tensor engine: J consecutive jobs per query tile when that saves tensor work (csrc/topk_tc16.cu)
     if (plan.J > 1 or plan.aligned) and tensor16_ok(bank, K, engine):
         tg, uent, upos = table.packed(j0, j1, plan.J, dev, plan.aligned)
@@ -518,6 +536,13 @@ def _affinity_topk_launch(bank, table, radius, K, mode, groups, engine, lists, j
             # which falls back to the CUDA-core engine
             if err.rc != _lib.ERR_UNSUPPORTED or engine != _lib.ENGINE_AUTO:
                 raise
+    if floor is not None:
+        call("fgvc_affinity_topk_seeded", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
+             ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
+             ctypes.c_void_p(floor.data_ptr() + 4 * lists.n_query * j0),
+             ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),
+             int(engine), stream_ptr())
+        return lists
     call("fgvc_affinity_topk", ptr(bank.buf), bank.fmt, bank.n_slots, bank.H, bank.W, bank.C,
          ctypes.c_void_p(jobs.data_ptr() + 16 * j0), j1 - j0, ptr(mem_feat), int(radius), mode, int(K), int(groups),
          ctypes.c_void_p(lists.val.data_ptr() + per_job * j0), ctypes.c_void_p(lists.idx.data_ptr() + per_job * j0),

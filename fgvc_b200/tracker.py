@@ -258,8 +258,14 @@ class VanillaTracker(nn.Module):
                 shared = engine.shared_pair_table(table, spans, T)
             if shared is not None:
                 utable, gmax, pair_ref = shared
+                # every list of a query frame t starts from the K-th best of the query's 5 x 5 neighbourhood in frame
+                # t - 1, which is in the memory of every group that is alive at t: without it the per-pair lists start
+                # cold and half of the launch is list insertion
+                floor = None
+                if os.environ.get("FGVC_NO_FLOOR") != "1" and radius >= 3:
+                    floor = engine.topk_floor(bank, utable, [j[0] - 1 for j in utable.jobs], radius, cfg.topk, mask_mode)
                 lists = engine.affinity_topk(bank, utable, radius, cfg.topk, mask_mode, groups=gmax,
-                                             engine=self.engine_id, pack=False)
+                                             engine=self.engine_id, pack=False, floor=floor)
                 pair_ref = torch.tensor(pair_ref, dtype=torch.int32, device=dev)
             else:
                 lists = engine.affinity_topk(bank, table, radius, cfg.topk, mask_mode, engine=self.engine_id)

@@ -164,6 +164,22 @@ FGVC_API int fgvc_affinity_topk(const void* feat_bank, int32_t bank_format, int3
                        int32_t radius, int32_t mask_mode, int32_t K, int32_t groups,
                        float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
 
+/* K1 with a starting floor for the lists (F16 bank, fp16 tensor engine; ignored by the other engines): floor[job][query
+ * pixel], in accumulator units (256 x cosine) as written by fgvc_topk_floor, must be a value that at least K genuine
+ * candidates of EVERY consumer of the job's lists reach -- the lists then hold only candidates above it, which is all
+ * a top-K merge needs.  For launches whose lists start cold and stay short: one list per (query frame, memory frame)
+ * pair shared between the point groups of a clip (vanilla_tracker.py:262-284 re-runs the whole sub-clip per group),
+ * where half of the launch was list insertion.  fgvc_topk_floor scores the 5 x 5 neighbourhood of the query's own
+ * position in ONE memory frame per job (seed_feat_slot[job]; < 0 = no floor for the job) exactly, in-image and in-mask
+ * keys only, and writes the K-th largest minus a rounding margin (-inf where fewer than K are valid). */
+FGVC_API int fgvc_affinity_topk_seeded(const void* feat_bank, int32_t bank_format, int32_t n_slots, int32_t H, int32_t W, int32_t C,
+                       const fgvc_job* jobs, int32_t n_jobs, const int32_t* mem_feat_slot,
+                       int32_t radius, int32_t mask_mode, int32_t K, int32_t groups, const float* floor,
+                       float* topk_val, int32_t* topk_idx, int32_t engine, void* stream);
+FGVC_API int fgvc_topk_floor(const void* feat_bank, int32_t bank_format, int32_t H, int32_t W, int32_t C,
+                       const fgvc_job* jobs, int32_t n_jobs, const int32_t* seed_feat_slot, int32_t radius,
+                       int32_t mask_mode, int32_t K, float* floor_out, void* stream);
+
 /* K1 on job-packed tiles (F16 bank, tcgen05 fp16 three-term engine only; local_attention.py:318-356 for several
  * consecutive frames of the loop vanilla_tracker.py:345-366 at once): same output as fgvc_affinity_topk
  * for the jobs named by the tile groups (lists are written at [job][list][Nq][K] by job index, `groups` lists per

@@ -752,3 +752,42 @@ def test_heatmap_coords_pruned_search_is_exact():
         assert (err < 0.02).all(), (out_hw, err)
         ref = O.img2coord_port(up[None].numpy())[:, :, 0].T          # the reference's own (tie order unspecified)
         assert np.abs(got - ref)[[0, 3, 6]].max() < 0.02      # maps without (near-)ties
+
+
+def test_topk_floor_is_a_valid_lower_bound_and_seeded_lists_merge_to_the_same_result():
+    """fgvc_topk_floor: the K-th best of the query's in-image, in-mask 5 x 5 neighbourhood in one memory frame, minus a
+    margin -- never above the job's true K-th affinity, -inf where fewer than K samples exist.  Seeded K1 lists hold
+    only candidates above the floor; after the gather the propagated labels are those of the unseeded launch."""
+    from fgvc_b200 import engine, _lib
+    g = torch.Generator().manual_seed(31)
+    T, C, H, W, L, K, r = 4, 64, 18, 22, 6, 10, 5
+    feats = _coherent(g, T, C, H, W).cuda()
+    bank = engine.FeatureBank(T, C, H, W, "cuda", split="f16")
+    bank.load_frames(feats, 0, normalize=True)
+    table = engine.JobTable()
+    table.add(3, [0, 1, 2], [0, 1, 2], 3)
+    table.add(2, [0, 1], [0, 1], 2)
+    floor = engine.topk_floor(bank, table, [2, -1], r, K, "circle")
+    assert floor.shape == (2, H * W) and bool(torch.isinf(floor[1]).all())
+    f = torch.nn.functional.normalize(feats.double(), dim=1)
+    aff = torch.einsum("cq,ck->qk", f[3].reshape(C, -1), f[2].reshape(C, -1))          # [Nq, Nk] vs frame 2
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    ys, xs = ys.reshape(-1).cuda(), xs.reshape(-1).cuda()
+    dy, dx = ys[:, None] - ys[None, :], xs[:, None] - xs[None, :]
+    near = (dy.abs() <= 2) & (dx.abs() <= 2) & (dy * dy + dx * dx < r * r)
+    kth_near = aff.masked_fill(~near, -float("inf")).topk(K, dim=1).values[:, -1]
+    have = near.sum(1) >= K
+    got = floor[0].double() / 256.0
+    assert bool(torch.isinf(got[~have]).all()) and bool((~have).any())                 # corners: fewer than K samples
+    assert bool((got[have] <= kth_near[have]).all())
+    assert float((kth_near[have] - got[have]).max()) < 1e-3                            # and tight: only the margin
+    labels = engine.LabelBank(T, L, H, W, "cuda")
+    lab0 = torch.rand(T, L, H, W, generator=g).cuda()
+    for t in range(3):
+        labels.put_nchw(lab0[t], t)
+    outs = []
+    for fl in (None, floor):
+        lists = engine.affinity_topk(bank, table, r, K, "circle", groups=3, pack=False, floor=fl)
+        engine.gather_labels(lists, table, 0, 1, labels, 0.07)
+        outs.append(labels.get_nchw(3).clone())
+    assert torch.equal(outs[0], outs[1])

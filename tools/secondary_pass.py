@@ -22,6 +22,10 @@ h, w = c["hw"]
 feats = bench._secondary_feats(c, dev, 1, seed0=2000)[0]
 qp = S.query_points(c["P"], c["T"], h, w, seed=1)
 groups = [(0, qp[:, 1:].to(dev))]
+if os.environ.get("SPREAD_GROUPS"):      # TAP-Vid query_mode='first': query times spread over [0, T/2)
+    n = int(os.environ["SPREAD_GROUPS"])
+    pts = qp[:, 1:].to(dev)
+    groups = [((c["T"] // 2) * g // n, pts[g::n]) for g in range(n)]
 cfg = dict(precede_frames=precede, topk=10, temperature=0.07, neighbor_range=c["nr"], with_first=True,
            with_first_neighbor=True)
 trk = fgvc_b200.VanillaTracker(backbone=torch.nn.Identity(), test_cfg=cfg)

@@ -541,7 +541,8 @@ def run_secondary(dev, rank, world, args):
         torch.cuda.empty_cache()
     if not args.only or "cfg3ii" in args.only:
         res["cfg3ii_c2f_tapvid_davis"] = run_c2f_clip(dev, rank, world)
-    return res
+    order = ["cfg3_tapvid_davis", "cfg3ii_c2f_tapvid_davis"]
+    return {k: res[k] for k in order + [k for k in res if k not in order] if k in res}
 
 
 def run_c2f_clip(dev, rank, world):

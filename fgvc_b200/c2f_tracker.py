@@ -46,24 +46,32 @@ class C2FPointTracker:
             self._copy_stream, self._k0_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         cp, k0 = self._copy_stream, self._k0_stream
         step = -(-T // n_chunks)
-        cp.wait_stream(cur)
-        k0.wait_stream(cur)
+        # two persistent staging buffers per stack (kept across calls): a copy waits only for the K0 that last read its buffer
+        key = (step,) + tuple(feats_coarse.shape[1:]) + tuple(feats_fine.shape[1:]) + (dev.index,)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage_c = [torch.empty((step,) + tuple(feats_coarse.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._stage_f = [torch.empty((step,) + tuple(feats_fine.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._stage_free, self._stage_key = [None, None], key
+            cp.wait_stream(cur)                           # fresh memory: earlier kernels of this stream may still use it
+        k0.wait_stream(cur)                               # the banks may still be read by the previous call's kernels
         done = []
-        for a in range(0, T, step):
+        for i, a in enumerate(range(0, T, step)):
             b = min(T, a + step)
+            fc, ff = self._stage_c[i % 2][:b - a], self._stage_f[i % 2][:b - a]
             with torch.cuda.stream(cp):
-                fc = feats_coarse[a:b].to(dev, non_blocking=True)
-                ff = feats_fine[a:b].to(dev, non_blocking=True)
+                if self._stage_free[i % 2] is not None:
+                    cp.wait_event(self._stage_free[i % 2])
+                fc.copy_(feats_coarse[a:b], non_blocking=True)
+                ff.copy_(feats_fine[a:b], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(cp)
             with torch.cuda.stream(k0):
                 k0.wait_event(ready)
-                coarse.load_frames(fc.float(), a, normalize=normalize)
-                fine.load_frames(ff.float(), a, normalize=normalize)
+                coarse.load_frames(fc, a, normalize=normalize)
+                fine.load_frames(ff, a, normalize=normalize)
                 ev = torch.cuda.Event()
                 ev.record(k0)
-            fc.record_stream(k0)
-            ff.record_stream(k0)
+            self._stage_free[i % 2] = ev
             done.append((b, ev))
         state = {"i": 0}
 
@@ -120,4 +128,5 @@ class C2FPointTracker:
             _lib.call("fgvc_labels_to_nchw", _lib.ptr(out), 0, labels.Lp, P, Hc * Wc, _lib.ptr(maps), _lib.stream_ptr())
             traj[t] = engine.heatmap_coords(maps, (h, w))
             outs.append(out)
+        landed(T - 1)            # (a one-frame clip: the banks must not be released under the staging stream)
         return traj, outs

@@ -473,11 +473,10 @@ def run_secondary(dev, rank, world, args):
             def one_pass(from_host):
                 outs = []
                 for ci in my_clips:
-                    if from_host and shard is None:
-                        f = feats_host[ci % n_distinct]       # pinned host tensor: staged in chunks by the tracker
-                    elif from_host:
-                        f = torch.empty_like(feats_list[ci % n_distinct])
-                        f.copy_(feats_host[ci % n_distinct], non_blocking=True)
+                    if from_host:
+                        # pinned host tensor: staged in chunks by the tracker (two-phase split: a rank uploads only the
+                        # frames its K1 jobs read)
+                        f = feats_host[ci % n_distinct]
                     else:
                         f = feats_list[ci % n_distinct]
                     traj = trk.propagate_points(f, groups, (h, w), shard=shard)[0]

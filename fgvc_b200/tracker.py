@@ -229,7 +229,7 @@ class VanillaTracker(nn.Module):
         shared = None
         rank, world = shard if shard is not None else (0, 1)
         streamed = host_feats and len(groups) == 1 and world == 1 and len(table) > 0
-        if host_feats and not streamed:
+        if host_feats and not streamed and world == 1:
             bank.load_frames(feats.to(dev, non_blocking=True), 0, normalize=normalize)
         if streamed:
             lists = self._stream_in(feats, bank, table, groups[0][0], radius, mask_mode, normalize)
@@ -244,6 +244,22 @@ class VanillaTracker(nn.Module):
                                   groups=shared[1] if shared is not None else None, pack=shared is None)
             lo, hi, per = apis.frame_shard(len(ktable), rank, world)
             lists = engine.TopKLists(per * world, plan.lists_per_job, Hf * Wf, cfg.topk, dev)
+            if host_feats:
+                # phase 1 only reads the frames of this rank's jobs (query frames + their memories) and phase 2 reads no
+                # features at all: a rank uploads and prepares ~T / world + precede frames instead of the whole clip
+                need = set()
+                for (q_slot, b, e, _) in ktable.jobs[lo:hi]:
+                    need.add(q_slot)
+                    need.update(r & ~_lib.MEM_UNMASKED for r in ktable.mem_feat[b:e])
+                need = sorted(need)
+                i = 0
+                while i < len(need):
+                    j = i
+                    while j + 1 < len(need) and need[j + 1] == need[j] + 1:
+                        j += 1
+                    a, b_ = need[i], need[j] + 1
+                    bank.load_frames(feats[a:b_].to(dev, non_blocking=True), a, normalize=normalize)
+                    i = j + 1
             if hi > lo:
                 engine.affinity_topk(bank, ktable, radius, cfg.topk, mask_mode, engine=self.engine_id, lists=lists,
                                      job_range=(lo, hi), plan=plan)

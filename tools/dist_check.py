@@ -39,6 +39,13 @@ def main():
         want2 = trk(test_mode=True, rgbs=rgbs2, query_points=qp2, trajectories=torch.zeros(1, T2, P2, 2),
                     visibilities=torch.zeros(1, T2, P2))
     err = max(err, (got2[2].double() - want2[2].double()).abs().max().item())
+    # host features through the two-phase split: every rank uploads only the frames its K1 jobs read
+    feats = trk.get_feats(rgbs2[0].cuda())
+    grp = [(0, qp2[0, :, 1:])]
+    with torch.no_grad():
+        a = trk.propagate_points(feats.cpu().pin_memory(), grp, (h, w), shard=(rank, world))[0]
+        b = trk.propagate_points(feats, grp, (h, w))[0]
+    err = max(err, (a - b).abs().max().item())
     trk.test_cfg = type(trk.test_cfg)(cfg)
     # video-sharded driver + typed NCCL gather
     ds = [dict(rgbs=S.synthetic_video(4, 32, 48, seed=10 + i)[None], query_points=S.query_points(3, 4, 32, 48, seed=i)[None],

@@ -214,7 +214,7 @@ class VanillaTracker(nn.Module):
             bank = pre_bank
         else:
             bank = FeatureBank(T, C, Hf, Wf, dev, split=cfg.get("split"))
-            if not host_feats:
+            if not host_feats and (shard is None or shard[1] == 1):
                 bank.load_frames(feats, 0, normalize=normalize)
 
         table = JobTable()
@@ -244,9 +244,10 @@ class VanillaTracker(nn.Module):
                                   groups=shared[1] if shared is not None else None, pack=shared is None)
             lo, hi, per = apis.frame_shard(len(ktable), rank, world)
             lists = engine.TopKLists(per * world, plan.lists_per_job, Hf * Wf, cfg.topk, dev)
-            if host_feats:
+            if pre_bank is None:
                 # phase 1 only reads the frames of this rank's jobs (query frames + their memories) and phase 2 reads no
-                # features at all: a rank uploads and prepares ~T / world + precede frames instead of the whole clip
+                # features at all: a rank uploads (host features) and prepares ~T / world + precede frames instead of
+                # the whole clip
                 need = set()
                 for (q_slot, b, e, _) in ktable.jobs[lo:hi]:
                     need.add(q_slot)

@@ -1,6 +1,8 @@
 // K1b: merge the per-group top-K lists, divide by the temperature, softmax over the K
 // winners and gather + weighted-sum the label rows (local_attention.py:356-374).
 // HBM/L2-bound: K label rows of Lp floats per query, read as float4, coalesced along L.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fgvc {
@@ -215,9 +217,63 @@ gather_chain_kernel(const float* __restrict__ cw, const int32_t* __restrict__ cr
   // this CTA's queries: a contiguous slice (the same for every job)
   const int per = (n_pix + gridDim.x - 1) / gridDim.x;
   const int q_lo = blockIdx.x * per, q_hi = min(n_pix, q_lo + per);
+  // single-pass slices (the usual case: the grid is sized for it): the label-independent (weight, row) pairs of job
+  // j + 1 are fetched into registers while job j is gathered, so the only loads after a grid barrier are the label rows
+  const bool one_pass = q_hi - q_lo <= CH_Q;
+  constexpr int PRE = (CH_Q * K + 255) / 256;
+  float pw[PRE];
+  int pr[PRE];
+  const int nq1 = max(q_hi - q_lo, 0);
+  if (one_pass) {
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+      const int i = tid + 256 * u;
+      if (i < nq1 * K) {
+        const int64_t o = ((int64_t)0 * n_pix + q_lo) * K + i;
+        (&sw[0][0])[i] = __ldg(cw + o);
+        (&srow[0][0])[i] = __ldg(crow + o);
+      }
+    }
+    __syncthreads();
+  }
   for (int j = 0; j < n_jobs; ++j) {
     const int out_slot = jobs[job_begin + j].out_slot;
     float4* dst = reinterpret_cast<float4*>(lab) + (int64_t)out_slot * n_pix * l4n;
+    if (one_pass) {
+      if (j + 1 < n_jobs) {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int i = tid + 256 * u;
+          if (i < nq1 * K) {
+            const int64_t o = ((int64_t)(j + 1) * n_pix + q_lo) * K + i;
+            pw[u] = __ldg(cw + o);
+            pr[u] = __ldg(crow + o);
+          }
+        }
+      }
+      for (int i = tid; i < nq1 * l4n; i += 256) {
+        const int q = i / l4n, c = i - q * l4n;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float w = sw[q][k];
+          if (w != 0.f) {
+            const float4 v = __ldcg(src + (int64_t)srow[q][k] * l4n + c);   // may have been written by another CTA
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+          }
+        }
+        dst[(int64_t)(q_lo + q) * l4n + c] = acc;
+      }
+      if (j + 1 < n_jobs) {
+        __syncthreads();                               // everyone is done with this job's pairs
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int i = tid + 256 * u;
+          if (i < nq1 * K) { (&sw[0][0])[i] = pw[u]; (&srow[0][0])[i] = pr[u]; }
+        }
+      }
+    } else
     for (int q0 = q_lo; q0 < q_hi; q0 += CH_Q) {
       const int nq = min(CH_Q, q_hi - q0);
       __syncthreads();
@@ -294,6 +350,8 @@ static int launch_chain_t(const float* tv, const int32_t* ti, int k_in, int grou
   // latency-bound (a few microseconds per frame): as many CTAs as can be co-resident, so that a CTA's slice is
   // one pass of <= CH_Q queries whenever possible
   // (short label rows: ~2 CTAs per SM; long rows want every resident thread for memory-level parallelism)
+  // (measured on the bench clip, 6420 queries x 3 float4: 301 CTAs 337 us; 148 CTAs 558 us -- two passes per CTA;
+  // 602 CTAs 379 us, 1184 CTAs 485 us -- the barrier grows)
   const int ctas = (int)min((int64_t)max_ctas, max((int64_t)1, ((int64_t)n_pix * l4n + 63) / 64));
   int n_jobs = n, jb = job_begin, npx = n_pix, lp = Lp;
   void* args[] = {(void*)&cw, (void*)&crow, (void*)&jobs, (void*)&jb, (void*)&n_jobs, (void*)&npx, (void*)&lab,

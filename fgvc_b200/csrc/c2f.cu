@@ -116,7 +116,7 @@ c2f_fine_kernel(const void* __restrict__ fine_bank, int Hc, int Wc, int Hf, int 
 
 constexpr int C2F_TAIL_QB = 8;      // coarse queries per CTA: a coarse grid is small, keep the grid wide
 
-// Tail of the tensor-core fine stage (topk_tc16w.cu): per coarse query, the K best in-window fine keys are in
+// Tail of the tensor-core fine stage (topk_tc16.cu): per coarse query, the K best in-window fine keys are in
 // tv / ti.  The reference's windows are zero padded (F.unfold(padding = rf), local_attention.py:790-793): every
 // window position outside the fine map is a candidate too, with affinity 0 and value 0 -- their number is
 // analytic, so they are inserted here; then soft-max over the K winners and the gather of fine label rows.

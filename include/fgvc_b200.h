@@ -291,8 +291,10 @@ FGVC_API int fgvc_point_clip_tail_shared(const float* topk_val, const int32_t* t
  * T*R^2, softmax, gather of FINE labels.  Output on the coarse grid: out[Hc*Wc][Lp].
  * job_dev / job_host: the same job in device memory (read by K1) and host memory (read by
  * the launcher); scratch_val / scratch_idx: fgvc_c2f_scratch_elems(n_mem, Hc*Wc) elements each (the coarse per-frame
- * arg-max table, then the fine top-K lists).  With an F16 fine bank (Cf % 64 == 0, Cf <= 256, n_mem <= 32) the fine
- * stage runs on the tensor cores as a window-mode K1 (csrc/topk_tc16w.cu); otherwise one warp per candidate. */
+ * arg-max table, one floor per coarse query, then the fine top-K lists).  With an F16 fine bank (Cf % 64 == 0,
+ * Cf <= 256, n_mem <= 64) the fine stage runs on the tensor cores as a window-mode K1 (csrc/topk_tc16.cu) whose lists
+ * start from the K-th best of the exactly scored window centres (+ 4 neighbours) of all memory frames; otherwise one
+ * warp per candidate. */
 FGVC_API int64_t fgvc_c2f_scratch_elems(int32_t n_mem, int32_t n_coarse);
 FGVC_API int fgvc_c2f_propagate(const void* coarse_bank, int32_t bank_format, int32_t n_slots, int32_t Hc, int32_t Wc,
                        int32_t C, const void* fine_bank, int32_t Hf, int32_t Wf, int32_t Cf,

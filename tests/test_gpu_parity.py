@@ -384,7 +384,7 @@ def test_c2f_matches_reference_golden(golden_dir, engine):
 
 @pytest.mark.parametrize("geom", [(6, 7, 4, 64, 64, 3, 5, 5), (9, 20, 4, 64, 128, 2, 6, 12), (5, 5, 2, 128, 64, 4, 3, 2)])
 def test_c2f_window_engine_matches_oracle(monkeypatch, geom):
-    """Fine stage on the tensor cores (csrc/topk_tc16w.cu: window-mode K1 + tail) against the oracle restatement
+    """Fine stage on the tensor cores (csrc/topk_tc16.cu: window-mode K1 + tail) against the oracle restatement
     of masked_attention_efficient_c2f (itself pinned to the genuine function by the CPU golden test) and against the
     one-warp-per-candidate kernel.  Small maps with a big radius_fine put most windows across the border, where the
     zero-padded positions (affinity 0, value 0) compete for the top-k."""

@@ -71,7 +71,7 @@ struct Params {
   float* dbg;
   int32_t* dbg_meta;
   int dbg_max_boxes;
-  int exp_flags;             // experiments (FGVC_TC16_EXP env): 1 = no candidate scan, 2 = no TMEM loads, 4 = half the TMA bytes
+  int exp_flags;             // experiments (FGVC_TC16_EXP env): 1 = no candidate scan, 4 = half the TMA bytes
 };
 
 // ------------------------------------------------------------------------- PTX wrappers (cta_group aware)
@@ -600,17 +600,20 @@ affinity_topk_tc16_kernel(const __grid_constant__ CUtensorMap tmap_k, const __ha
         uint32_t bits[ROWS];
         bool hot[ROWS];
         const bool dump = !WIN && p.dbg != nullptr && (int)seq < p.dbg_max_boxes;
+        // per box: the lane's centre relative to the box, the last in-image column of the box, the rows of the box
+        // that exist (in the box and in the image).  With bx >= 0: max(max(cx - hw, 0) - bx, 0) = max(cx - bx - hw, 0),
+        // and a sentinel half width of -1 gives hi < lo by itself.
+        const int cbx = cx - bx, wlim = min(p.W - 1 - bx, 15), rows_ok = min(p.BH, p.H - by), dy0 = by + wg - cy;
 #pragma unroll
         for (int rr = 0; rr < ROWS; ++rr) {
           const int row = wg + EPI_WG * rr;
-          const int ky = by + row;
           int hw = p.W;
-          if (masked) hw = halfw[min(abs(ky - cy), hw_n + 1)];
-          const int lo = max(max(cx - hw, 0) - bx, 0);
-          const int hi = min(min(cx + hw, p.W - 1) - bx, 15);
-          const bool ok = row < p.BH;
-          bits[rr] = (ok && mine && hw >= 0 && hi >= lo && ky < p.H) ? ((2u << hi) - (1u << lo)) : 0u;
-          hot[rr] = ok && (__any_sync(0xffffffffu, bits[rr] != 0) || dump) && !(p.exp_flags & 2);   // warp-uniform
+          if (masked) hw = halfw[min(abs(dy0 + EPI_WG * rr), hw_n + 1)];
+          const int lo = max(cbx - hw, 0);
+          const int hi = min(cbx + hw, wlim);
+          const bool ok = row < rows_ok;                                    // warp-uniform
+          bits[rr] = (ok && mine && hi >= lo) ? ((2u << hi) - (1u << lo)) : 0u;
+          hot[rr] = ok && (__any_sync(0xffffffffu, bits[rr] != 0) || dump);    // warp-uniform
         }
         if (!in_flight) {
           mbar_wait_sleep(tfull_bar + buf, (tpar >> buf) & 1u);

@@ -423,6 +423,24 @@ def shared_pair_table(table, spans, T):
     return utable, gmax, pair_ref
 
 
+def frame_runs(table, j0, j1):
+    """Maximal runs [a, b) of feature slots that the jobs [j0, j1) of ``table`` read (their query frames and memory
+    frames): what a rank of the two-phase split has to upload and prepare."""
+    need = set()
+    for (q_slot, b, e, _) in table.jobs[j0:j1]:
+        need.add(q_slot)
+        need.update(r & ~_lib.MEM_UNMASKED for r in table.mem_feat[b:e])
+    need = sorted(need)
+    runs, i = [], 0
+    while i < len(need):
+        j = i
+        while j + 1 < len(need) and need[j + 1] == need[j] + 1:
+            j += 1
+        runs.append((need[i], need[j] + 1))
+        i = j + 1
+    return runs
+
+
 def chain_workspace(dev, n_jobs, n_pix, K, flags=0, force=False):
     """(pointer, bytes) of the scratch that lets a clip tail run its gather chain as one persistent kernel;
     (None, 0) = per-frame launches (hard propagation decodes between frames, single-frame ranges gain nothing)."""

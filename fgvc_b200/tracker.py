@@ -248,19 +248,8 @@ class VanillaTracker(nn.Module):
                 # phase 1 only reads the frames of this rank's jobs (query frames + their memories) and phase 2 reads no
                 # features at all: a rank uploads (host features) and prepares ~T / world + precede frames instead of
                 # the whole clip
-                need = set()
-                for (q_slot, b, e, _) in ktable.jobs[lo:hi]:
-                    need.add(q_slot)
-                    need.update(r & ~_lib.MEM_UNMASKED for r in ktable.mem_feat[b:e])
-                need = sorted(need)
-                i = 0
-                while i < len(need):
-                    j = i
-                    while j + 1 < len(need) and need[j + 1] == need[j] + 1:
-                        j += 1
-                    a, b_ = need[i], need[j] + 1
+                for a, b_ in engine.frame_runs(ktable, lo, hi):
                     bank.load_frames(feats[a:b_].to(dev, non_blocking=True), a, normalize=normalize)
-                    i = j + 1
             if hi > lo:
                 engine.affinity_topk(bank, ktable, radius, cfg.topk, mask_mode, engine=self.engine_id, lists=lists,
                                      job_range=(lo, hi), plan=plan)

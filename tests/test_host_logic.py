@@ -372,3 +372,32 @@ def test_plan_chunks_cover_all_jobs_with_full_waves():
     ch = engine.plan_chunks(63, 56)
     waste = sum(-(-(b - a) * 56 // 148) for a, b in ch) / (63 * 56 / 148)
     assert waste < 1.15 and (ch[0][1] - ch[0][0]) <= 16 and len(ch) >= 3   # full waves, early start, overlap
+
+
+def test_frame_runs_of_a_job_range():
+    """Two-phase split: a rank reads its jobs' query frames, their memory windows and frame 0 -- nothing else."""
+    from fgvc_b200 import engine, _lib
+    t = engine.JobTable()
+    for f in range(1, 40):
+        mem = engine.memory_frames(f, 5, True)
+        t.add(f, mem, mem, f, unmasked=1)
+    assert engine.frame_runs(t, 0, len(t)) == [(0, 40)]
+    assert engine.frame_runs(t, 19, 29) == [(0, 1), (15, 30)]          # jobs 19..28 = frames 20..29, windows from 15
+    assert engine.frame_runs(t, 0, 3) == [(0, 4)]
+    assert engine.frame_runs(t, 5, 5) == []
+    covered = set()
+    for r in range(4):
+        lo, hi = r * 10, min(39, r * 10 + 10)
+        for a, b in engine.frame_runs(t, lo, hi):
+            covered.update(range(a, b))
+    assert covered == set(range(40))
+
+
+def test_in_mask_pairs_square_and_circle():
+    import bench
+    H, W, r = 9, 7, 2
+    brute_c = sum(1 for y in range(H) for x in range(W) for v in range(H) for u in range(W)
+                  if (y - v) ** 2 + (x - u) ** 2 < r * r)
+    brute_s = sum(1 for y in range(H) for x in range(W) for v in range(H) for u in range(W)
+                  if abs(y - v) <= r and abs(x - u) <= r)
+    assert bench.in_mask_pairs(H, W, r) == brute_c and bench.in_mask_pairs(H, W, r, square=True) == brute_s

@@ -209,10 +209,14 @@ __device__ __forceinline__ void warp_topk(const TopK<CK>& top, int topk, float* 
 // step 2 for one hot pixel: list the cells it is a tap of (each cell from its first hot tap only) with their output
 // ranges in the warp's shared list; a cell that does not fit is evaluated on the spot
 constexpr int CELL_CAP = 128;
+// (only outputs that reach tau can be winners: the lists then see a handful of insertions instead of filling up)
 __device__ __forceinline__ void eval_cell(const BilinearSrc& src, int y0, int y1, int x0, int x1, int out_w,
-                                          TopK<CK>& top) {
+                                          float tau_safe, TopK<CK>& top) {
   for (int oy = y0; oy <= y1; ++oy)
-    for (int ox = x0; ox <= x1; ++ox) push_key(top, src.at(oy, ox), oy * out_w + ox);
+    for (int ox = x0; ox <= x1; ++ox) {
+      const float v = src.at(oy, ox);
+      if (v >= tau_safe) push_key(top, v, oy * out_w + ox);
+    }
 }
 __device__ __forceinline__ void list_hot_cells(const BilinearSrc& src, int i, float tau_safe, int out_h, int out_w,
                                                uint2* cells, int* n_cells, TopK<CK>& top) {
@@ -232,7 +236,7 @@ __device__ __forceinline__ void list_hot_cells(const BilinearSrc& src, int i, fl
     if (lerp_coord(y0, src.sy, H).i0 != i0 || lerp_coord(x0, src.sx, W).i0 != j0) continue;   // cell without outputs
     const int slot = (out_h <= 65535 && out_w <= 65535) ? atomicAdd(n_cells, 1) : CELL_CAP;
     if (slot < CELL_CAP) cells[slot] = make_uint2((uint32_t)y0 | ((uint32_t)y1 << 16), (uint32_t)x0 | ((uint32_t)x1 << 16));
-    else eval_cell(src, y0, y1, x0, x1, out_w, top);
+    else eval_cell(src, y0, y1, x0, x1, out_w, tau_safe, top);
   }
 }
 
@@ -365,13 +369,14 @@ heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, 
       const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
       for (int k = lane; k < cnt; k += 32) {
         const int oy = y0 + k / nx, ox = x0 + k % nx;
-        push_key(top, src.at(oy, ox), oy * out_w + ox);
+        const float v = src.at(oy, ox);
+        if (v >= tau_safe) push_key(top, v, oy * out_w + ox);
       }
     }
   } else {
     for (int c = lane; c < nc; c += 32) {
       const uint2 r = cells[c];
-      eval_cell(src, r.x & 0xffff, r.x >> 16, r.y & 0xffff, r.y >> 16, out_w, top);
+      eval_cell(src, r.x & 0xffff, r.x >> 16, r.y & 0xffff, r.y >> 16, out_w, tau_safe, top);
     }
   }
   warp_topk(top, topk, win_v, win_i);

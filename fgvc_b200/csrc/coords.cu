@@ -244,7 +244,7 @@ constexpr int MAPS_PER_CTA = 8;
 constexpr int SLOTS = 32;          // per-lane slot maxima kept in shared memory (4 KB per map)
 
 // blockDim.x / 32 maps per CTA (<= MAPS_PER_CTA)
-__global__ void __launch_bounds__(32 * MAPS_PER_CTA)
+__global__ void __launch_bounds__(32 * MAPS_PER_CTA, 4)
 heatmap_coords_kernel(const float* __restrict__ maps, int n_maps, int H, int W, int out_h, int out_w, int topk,
                       float* __restrict__ out_xy) {
   __shared__ float win_v_s[MAPS_PER_CTA][CK];

@@ -269,7 +269,13 @@ class VanillaTracker(nn.Module):
                 # cold and half of the launch is list insertion
                 floor = None
                 if os.environ.get("FGVC_NO_FLOOR") != "1" and radius >= 3:
-                    floor = engine.topk_floor(bank, utable, [j[0] - 1 for j in utable.jobs], radius, cfg.topk, mask_mode)
+                    # the newest frame that EVERY job of a query frame has in its memory (-1: none, no floor)
+                    common = {}
+                    for (q_slot, b, e, _) in table.jobs:
+                        mem = {r & ~_lib.MEM_UNMASKED for r in table.mem_feat[b:e]}
+                        common[q_slot] = mem if q_slot not in common else (common[q_slot] & mem)
+                    seeds = [max(common.get(j[0], set()), default=-1) for j in utable.jobs]
+                    floor = engine.topk_floor(bank, utable, seeds, radius, cfg.topk, mask_mode)
                 lists = engine.affinity_topk(bank, utable, radius, cfg.topk, mask_mode, groups=gmax,
                                              engine=self.engine_id, pack=False, floor=floor)
                 pair_ref = torch.tensor(pair_ref, dtype=torch.int32, device=dev)

@@ -456,6 +456,14 @@ def test_shared_lists_across_groups_equal_per_group_k1(monkeypatch):
     for a, b in zip(shared, plain):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) < 1e-3            # exact ties may enter the lists in another order
+    # memory = the first frame only: the groups of a query frame have no frame in common, so no list floor applies
+    trk0 = fgvc_b200.VanillaTracker(backbone=torch.nn.Identity(), test_cfg=dict(cfg, precede_frames=0))
+    shared0 = trk0.propagate_points(feats, groups, (Hf * stride, Wf * stride))
+    monkeypatch.setenv("FGVC_NO_SHARE", "1")
+    plain0 = trk0.propagate_points(feats, groups, (Hf * stride, Wf * stride))
+    monkeypatch.delenv("FGVC_NO_SHARE", raising=False)
+    for a, b in zip(shared0, plain0):
+        assert float((a - b).abs().max()) < 1e-3
 
 
 def test_forward_test_contract_and_oracle():

@@ -61,10 +61,10 @@ prep_features_kernel(const float* __restrict__ src, int64_t frame_stride, int64_
   }
   __syncthreads();
   const int64_t slot_off = (int64_t)(first_slot + frame) * feat_slot_floats(n_pix, C);
-  // two consecutive channels per thread: 4-byte (fp16 pair) / 8-byte (fp32 pair) stores
-  const int c2n = C / 2;
-  for (int i = threadIdx.x; i < 32 * c2n; i += 256) {
-    const int pp = i / c2n, c = 2 * (i - pp * c2n);
+  // two consecutive channels per thread: 4-byte (fp16 pair) / 8-byte (fp32 pair) stores; a warp walks the channel
+  // pairs of one pixel (no index division), 4 pixels per warp
+  for (int pp = warp; pp < 32; pp += 8)
+  for (int c = 2 * lane; c < C; c += 64) {
     const int p = p0 + pp;
     if (p < n_pix) {
       const float x0 = tile[c * 33 + pp] * inv[pp];

@@ -532,29 +532,33 @@ decode_minmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restr
   }
 }
 
+// One CTA = a 64 x 4 tile of output pixels of one frame (blockIdx.z): no index division, neighbouring threads share
+// their source taps.  Per-channel constants in shared memory as (min, max, reciprocal of the range, -).
 __global__ void __launch_bounds__(256)
 decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int L,
                           int Lp, int H, int W, int out_h, int out_w, const uint32_t* __restrict__ minmax,
                           uint8_t* __restrict__ masks) {
-  extern __shared__ float smm[];       // [2L] decoded min / max, [L] reciprocal of the range
-  float* srcp = smm + 2 * L;
-  const uint32_t* mm = minmax + (int64_t)blockIdx.y * 2 * L;
-  for (int i = threadIdx.x; i < 2 * L; i += 256) smm[i] = key2f(__ldg(mm + i));
+  extern __shared__ float4 scst[];     // [L] (min, max, 1 / ((max - min) + 1e-12), 0)
+  const uint32_t* mm = minmax + (int64_t)blockIdx.z * 2 * L;
+  for (int i = threadIdx.x; i < L; i += 256) {
+    const float mn = key2f(__ldg(mm + i)), mx = key2f(__ldg(mm + L + i));
+    scst[i] = make_float4(mn, mx, __frcp_rn((mx - mn) + 1e-12f), 0.f);
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < L; i += 256) srcp[i] = __frcp_rn((smm[L + i] - smm[i]) + 1e-12f);
-  __syncthreads();
-  const int o = blockIdx.x * 256 + threadIdx.x;
-  if (o >= out_h * out_w) return;
-  const int slot = jobs[job_begin + blockIdx.y].out_slot;
+  const int ox = blockIdx.x * 64 + (threadIdx.x & 63), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (ox >= out_w || oy >= out_h) return;
+  const int slot = jobs[job_begin + blockIdx.z].out_slot;
   const float4* src = reinterpret_cast<const float4*>(lab + (int64_t)slot * H * W * Lp);
   const int l4n = Lp / 4;
-  const int oy = o / out_w, ox = o - oy * out_w;
   const Tap t = make_tap(oy, ox, H, W, (float)H / (float)out_h, (float)W / (float)out_w);
-  float best = -INFINITY;
+  const float4* s00 = src + (int64_t)t.p00 * l4n;
+  const float4* s01 = src + (int64_t)t.p01 * l4n;
+  const float4* s10 = src + (int64_t)t.p10 * l4n;
+  const float4* s11 = src + (int64_t)t.p11 * l4n;
+  float best = -INFINITY, bar = -INFINITY;             // bar = best - 1e-6
   int arg = 0;
   for (int l4 = 0; l4 < l4n; ++l4) {
-    const float4 a = __ldg(src + (int64_t)t.p00 * l4n + l4), b = __ldg(src + (int64_t)t.p01 * l4n + l4);
-    const float4 c = __ldg(src + (int64_t)t.p10 * l4n + l4), d = __ldg(src + (int64_t)t.p11 * l4n + l4);
+    const float4 a = __ldg(s00 + l4), b = __ldg(s01 + l4), c = __ldg(s10 + l4), d = __ldg(s11 + l4);
     const float v4[4] = {tap_val(t, a.x, b.x, c.x, d.x), tap_val(t, a.y, b.y, c.y, d.y),
                          tap_val(t, a.z, b.z, c.z, d.z), tap_val(t, a.w, b.w, c.w, d.w)};
 #pragma unroll
@@ -562,19 +566,19 @@ decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restr
       const int l = 4 * l4 + k;
       if (l < L) {
         float v = v4[k];
-        const float mn = smm[l], mx = smm[L + l];
-        if (mx > 0.f) {
+        const float4 cs = scst[l];
+        if (cs.y > 0.f) {
           // The exact (correctly rounded) division is only needed for channels that can still win: the product
           // with the rounded reciprocal is within 2 ulp of the quotient (which lies in [0, 1]), so a channel whose
           // product is more than 1e-6 below the best exact quotient so far cannot reach it.  Same arg-max, bit for bit.
-          if ((v - mn) * srcp[l] < best - 1e-6f) continue;
-          v = __fdiv_rn(v - mn, (mx - mn) + 1e-12f);
+          if ((v - cs.x) * cs.z < bar) continue;
+          v = __fdiv_rn(v - cs.x, (cs.y - cs.x) + 1e-12f);
         }
-        if (v > best) { best = v; arg = l; }
+        if (v > best) { best = v; bar = v - 1e-6f; arg = l; }
       }
     }
   }
-  masks[(int64_t)slot * out_h * out_w + o] = (uint8_t)arg;
+  masks[((int64_t)slot * out_h + oy) * out_w + ox] = (uint8_t)arg;
 }
 
 // min keys are initialised to 0xffffffff and max keys to 0 by init_minmax_kernel
@@ -589,12 +593,12 @@ int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin
   if (n <= 0) return FGVC_OK;
   init_minmax_kernel<<<cdiv(n * 2 * L, 256), 256, 0, st>>>(minmax, n, L);
   FGVC_LAUNCH_CHECK();
-  dim3 grid(cdiv(out_h * out_w, 256), n), grid_cells(cdiv(H * W, 256), n);
+  dim3 grid(cdiv(out_w, 64), cdiv(out_h, 4), n), grid_cells(cdiv(H * W, 256), n);
   decode_minmax_jobs_kernel<<<grid_cells, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w,
                                                                minmax);
   FGVC_LAUNCH_CHECK();
-  decode_argmax_jobs_kernel<<<grid, 256, 3 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
-                                                         masks);
+  decode_argmax_jobs_kernel<<<grid, 256, L * 16, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
+                                                      masks);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }

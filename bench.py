@@ -218,14 +218,17 @@ def measure_h2d(dev, world, nbytes=256 << 20, reps=4):
     torch.cuda.synchronize()
     if world > 1:
         _dist().barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        devb.copy_(host, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
-    return nbytes * reps / (ms / 1e3) / 1e9
+    best = 0.0
+    for _ in range(3):                         # a ceiling: the best of three rounds (the link rate varies by ~15 %)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            devb.copy_(host, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+        best = max(best, nbytes * reps / (ms / 1e3) / 1e9)
+    return best
 
 
 class MaskGather:

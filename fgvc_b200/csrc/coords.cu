@@ -538,11 +538,19 @@ __global__ void __launch_bounds__(256)
 decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restrict__ jobs, int job_begin, int L,
                           int Lp, int H, int W, int out_h, int out_w, const uint32_t* __restrict__ minmax,
                           uint8_t* __restrict__ masks) {
-  extern __shared__ float4 scst[];     // [L] (min, max, 1 / ((max - min) + 1e-12), 0)
+  // [Lp] (min, divisor, reciprocal of the divisor, -) with divisor = (max - min) + 1e-12.  Channels that are not
+  // normalised (max <= 0: the map stays as it is) get (0, 1, 1): (v - 0) / 1 = v exactly; the pad channels get
+  // min = +inf: their value becomes -inf and can never win.  The inner loop then has no per-channel case split.
+  extern __shared__ float4 scst[];
   const uint32_t* mm = minmax + (int64_t)blockIdx.z * 2 * L;
-  for (int i = threadIdx.x; i < L; i += 256) {
-    const float mn = key2f(__ldg(mm + i)), mx = key2f(__ldg(mm + L + i));
-    scst[i] = make_float4(mn, mx, __frcp_rn((mx - mn) + 1e-12f), 0.f);
+  for (int i = threadIdx.x; i < Lp; i += 256) {
+    float4 cs = make_float4(INFINITY, 1.f, 1.f, 0.f);
+    if (i < L) {
+      const float mn = key2f(__ldg(mm + i)), mx = key2f(__ldg(mm + L + i));
+      const float dv = (mx - mn) + 1e-12f;
+      cs = mx > 0.f ? make_float4(mn, dv, __frcp_rn(dv), 0.f) : make_float4(0.f, 1.f, 1.f, 0.f);
+    }
+    scst[i] = cs;
   }
   __syncthreads();
   const int ox = blockIdx.x * 64 + (threadIdx.x & 63), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
@@ -564,18 +572,14 @@ decode_argmax_jobs_kernel(const float* __restrict__ lab, const fgvc_job* __restr
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int l = 4 * l4 + k;
-      if (l < L) {
-        float v = v4[k];
-        const float4 cs = scst[l];
-        if (cs.y > 0.f) {
-          // The exact (correctly rounded) division is only needed for channels that can still win: the product
-          // with the rounded reciprocal is within 2 ulp of the quotient (which lies in [0, 1]), so a channel whose
-          // product is more than 1e-6 below the best exact quotient so far cannot reach it.  Same arg-max, bit for bit.
-          if ((v - cs.x) * cs.z < bar) continue;
-          v = __fdiv_rn(v - cs.x, (cs.y - cs.x) + 1e-12f);
-        }
-        if (v > best) { best = v; bar = v - 1e-6f; arg = l; }
-      }
+      const float4 cs = scst[l];
+      // The exact (correctly rounded) division is only needed for channels that can still win: the product
+      // with the rounded reciprocal is within 2 ulp of the quotient (which lies in [0, 1]), so a channel whose
+      // product is more than 1e-6 below the best exact quotient so far cannot reach it.  Same arg-max, bit for bit.
+      const float num = v4[k] - cs.x;
+      if (num * cs.z < bar) continue;
+      const float v = __fdiv_rn(num, cs.y);
+      if (v > best) { best = v; bar = v - 1e-6f; arg = l; }
     }
   }
   masks[((int64_t)slot * out_h + oy) * out_w + ox] = (uint8_t)arg;
@@ -597,8 +601,8 @@ int launch_decode_jobs(const float* lab, const fgvc_job* jobs_dev, int job_begin
   decode_minmax_jobs_kernel<<<grid_cells, 256, 2 * L * 4, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w,
                                                                minmax);
   FGVC_LAUNCH_CHECK();
-  decode_argmax_jobs_kernel<<<grid, 256, L * 16, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
-                                                      masks);
+  decode_argmax_jobs_kernel<<<grid, 256, Lp * 16, st>>>(lab, jobs_dev, job_begin, L, Lp, H, W, out_h, out_w, minmax,
+                                                       masks);
   FGVC_LAUNCH_CHECK();
   return FGVC_OK;
 }

@@ -132,7 +132,94 @@ c2f_tail_kernel(const float* __restrict__ tv, const int32_t* __restrict__ ti, in
   const int tid = threadIdx.x;
   const int nc = Hc * Wc, nf = Hf * Wf;
   const int n_mem = job.mem_end - job.mem_begin;
-  if (tid < QB) {
+  __shared__ float sv[QB][K];
+  __shared__ int sid[QB][K];
+  if (n_lists <= 32) {
+    // one warp per coarse query: lane l holds partial list l (sorted by K1; all its loads in flight together); K
+    // rounds of a warp-wide arg-max over the list heads give the K best in the order the serial merge below finds
+    // them (equal values: lower list first, then list order); the analytic number of zero-padded candidates is a
+    // warp reduction; lane 0 finishes with the soft-max in the reference's summation order.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q = q0 + warp;                      // QB == 8 warps
+    float lv[K];
+    int li[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) { lv[i] = -INFINITY; li[i] = -1; }
+    if (q < nc && lane < n_lists) {
+      const int64_t o = ((int64_t)q * n_lists + lane) * k_in;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (i < k_in) { lv[i] = __ldg(tv + o + i); li[i] = __ldg(ti + o + i); }
+    }
+    int n_zero = 0;
+    if (q < nc) {
+      const int R = 2 * rf + 1;
+      for (int t = lane; t < n_mem; t += 32) {
+        const int bq = max(__ldg(best_idx + (int64_t)t * nc + q), 0) % nc;
+        const int cy = (bq / Wc) * scale, cx = (bq % Wc) * scale;
+        const int rows = min(cy + rf, Hf - 1) - max(cy - rf, 0) + 1, cols = min(cx + rf, Wf - 1) - max(cx - rf, 0) + 1;
+        n_zero += R * R - rows * cols;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_zero += __shfl_xor_sync(0xffffffffu, n_zero, o);
+    const int nz = min(n_zero, K);
+    int head = 0;
+    float myv = -INFINITY;                        // lane r keeps the r-th best genuine candidate
+    int myid = -1;
+    for (int r = 0; r < K; ++r) {
+      float v = -INFINITY;
+      int id = -1;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (j == head) { v = lv[j]; id = li[j]; }
+      if (id < 0) v = -INFINITY;                  // (a list ends at its first empty slot)
+      int from = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+        const int of = __shfl_xor_sync(0xffffffffu, from, o);
+        if (ov > v || (ov == v && of < from)) { v = ov; id = oi; from = of; }
+      }
+      if (v == -INFINITY) id = -1;
+      if (lane == from && id >= 0) ++head;
+      if (lane == r) { myv = v; myid = id; }
+    }
+    // zero-padded candidates (affinity 0, value 0) go behind the genuine ones that are >= 0
+    const int n_pos = __popc(__ballot_sync(0xffffffffu, lane < K && myid >= 0 && myv >= 0.f));
+    const int src_lane = lane < n_pos ? lane : max(lane - nz, 0);
+    float fv = __shfl_sync(0xffffffffu, myv, src_lane);
+    int fid = __shfl_sync(0xffffffffu, myid, src_lane);
+    if (lane >= n_pos && lane < n_pos + nz) { fv = 0.f; fid = -2; }      // id -2: padded candidate, value row of zeros
+    if (lane < K) { sv[warp][lane] = fv; sid[warp][lane] = fid; }
+    __syncwarp();
+    if (lane == 0) {
+      float a[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) a[i] = __fdiv_rn(sv[warp][i], temperature);
+      const float mx = a[0];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        a[i] = (i < k_in && sid[warp][i] != -1) ? expf(a[i] - mx) : 0.f;
+        sum += a[i];
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int id = sid[warp][i];
+        const bool live = i < k_in && id != -1;
+        sw[warp][i] = live ? __fdiv_rn(a[i], sum) : 0.f;
+        int row = -1;
+        if (live && id >= 0) {
+          const int pos = id / nf;
+          row = __ldg(mem_label + job.mem_begin + pos) * nf + (id - pos * nf);
+        }
+        srow[warp][i] = row;                      // row < 0: contributes value 0 (but its weight took soft-max mass)
+      }
+    }
+  }
+  if (n_lists > 32 && tid < QB) {
     const int q = q0 + tid;
     TopK<K> top;
     top.init();
